@@ -1,0 +1,116 @@
+/* mathmap_b200 — C ABI of the B200-native evaluation backend for MathMap's
+ * per-pixel render path.
+ *
+ * This header is the drop-in boundary: plain C, pointers and sizes only.  Each
+ * entry point names the reference interface it replaces (paths into the
+ * reference tree).  INTEGRATION.md shows the backends/cuda.c a maintainer adds
+ * to the reference to bind these.
+ *
+ * Everything that renders requires a CUDA device and fails loudly (returns
+ * nonzero / NULL and sets mmb_last_error) without one.  There is no CPU path.
+ */
+#ifndef MATHMAP_B200_H
+#define MATHMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mmb_module mmb_module;         /* a compiled filter module; reference: mathmap_t after compile_mathmap */
+typedef struct mmb_invocation mmb_invocation; /* reference: mathmap_invocation_t */
+
+/* userval kinds, reference userval.h USERVAL_* */
+enum { MMB_USERVAL_INT = 0, MMB_USERVAL_FLOAT = 1, MMB_USERVAL_BOOL = 2, MMB_USERVAL_COLOR = 3,
+       MMB_USERVAL_CURVE = 4, MMB_USERVAL_GRADIENT = 5, MMB_USERVAL_IMAGE = 6 };
+/* edge behaviour, reference mathmap.h EDGE_BEHAVIOUR_* */
+enum { MMB_EDGE_COLOR = 0, MMB_EDGE_WRAP = 1, MMB_EDGE_REFLECT = 2, MMB_EDGE_ROTATE = 3 };
+#define MMB_CURVE_POINTS 1024 /* reference userval.h USER_CURVE_POINTS */
+
+/* ---- compile ---------------------------------------------------------------
+ * mmb_compile: MathMap source -> optimised IR -> CUDA C.  Replaces
+ *   compile_mathmap (mathmap_common.c:504-580) = parse_mathmap +
+ *   compiler_compile_filters + gen_and_load_c_code.
+ * mmb_load_ir: the same from IR text ("mmir 1", see csrc/ir/ir_text.cpp) that a
+ *   reference-side backends/cuda.c prints from filter_code_t**.  Replaces
+ *   gen_and_load_c_code (backends/cc.c:634-758, declared compiler.h:79-82).
+ * Both return NULL on error with the message in mmb_last_error().  NVRTC
+ * compilation for sm_100a happens lazily at the first render of a given
+ * sampler/edge/output configuration.
+ */
+mmb_module *mmb_compile(const char *source);
+mmb_module *mmb_load_ir(const char *ir_text);
+void mmb_module_free(mmb_module *m); /* unload_c_code, backends/cc.c:761 */
+const char *mmb_module_ir(const mmb_module *m);          /* optimised IR as text */
+const char *mmb_module_cuda_source(mmb_module *m);       /* generated CUDA C for the default configuration */
+const char *mmb_module_main_filter_name(const mmb_module *m);
+int mmb_module_num_uservals(const mmb_module *m);        /* uservals of the main filter, userval_info_t list */
+int mmb_module_userval_info(const mmb_module *m, int index, char *name, size_t name_len, int *type, float *min_value,
+                            float *max_value, float *default_value);
+int mmb_module_userval_index(const mmb_module *m, const char *name);
+
+/* ---- invoke ----------------------------------------------------------------
+ * mmb_invoke replaces invoke_mathmap (mathmap_common.c:747-790): output 4 bytes
+ * per pixel, edge behaviour COLOR with colour 0, nearest sampling, no
+ * supersampling, uservals at their defaults, R = sqrt(2).  `device` is the CUDA
+ * device ordinal.
+ */
+mmb_invocation *mmb_invoke(mmb_module *m, int img_width, int img_height, int device);
+void mmb_invocation_free(mmb_invocation *inv);
+int mmb_set_antialiasing(mmb_invocation *inv, int enabled);   /* invocation_set_antialiasing, mathmap_common.c:737 (-i flag) */
+int mmb_set_supersampling(mmb_invocation *inv, int enabled);  /* invocation->supersampling (-o flag) */
+int mmb_set_edge_behaviour(mmb_invocation *inv, int mode_x, int mode_y, uint32_t color_x, uint32_t color_y);
+int mmb_set_output_bpp(mmb_invocation *inv, int bpp);         /* invocation->output_bpp: 1, 2, 3 or 4 */
+int mmb_set_precise_math(mmb_invocation *inv, int enabled);   /* 1: libm calls in double like the host; 0 (default): CUDA float libm */
+
+/* userval bindings, reference userval.h userval_t / mathmap_cmdline.c:756-796 (-D name=value) */
+int mmb_set_userval_int(mmb_invocation *inv, int index, int value);
+int mmb_set_userval_float(mmb_invocation *inv, int index, float value);
+int mmb_set_userval_bool(mmb_invocation *inv, int index, int value);
+int mmb_set_userval_color(mmb_invocation *inv, int index, float r, float g, float b, float a);
+int mmb_set_userval_curve(mmb_invocation *inv, int index, const float *values /* MMB_CURVE_POINTS */);
+int mmb_set_userval_gradient(mmb_invocation *inv, int index, const uint32_t *rgba_packed /* MMB_CURVE_POINTS, R in the high byte */);
+/* input drawables are RGBA8, rows top to bottom, R first (color.h:36-43 packing is applied on load).
+ * _host copies to the device; _device adopts a device pointer owned by the caller (e.g. an NCCL-broadcast buffer). */
+int mmb_set_userval_image_host(mmb_invocation *inv, int index, const uint8_t *rgba, int width, int height);
+int mmb_set_userval_image_device(mmb_invocation *inv, int index, const void *device_rgba, int width, int height);
+
+/* ---- render ------------------------------------------------------------------
+ * mathfuncs_t {init_frame, init_slice, calc_lines} (compiler.h:50-66, drawable.h:57-60).
+ * mmb_init_frame: frame-constant values are computed once on the host and
+ *   native filters / render() run as kernels; reference init_frame_<f>
+ *   (new_template.c.in:314-337) via invocation_new_frame (mathmap_common.c:798).
+ * mmb_calc_lines: rows [first_row, last_row) of the region, one launch for the
+ *   band; q is a HOST buffer laid out like the reference's (row stride
+ *   width*bpp, or float[4] per pixel when floatmap != 0); the device result is
+ *   copied into it.  Reference calc_lines_<f> (new_template.c.in:208-312).
+ * mmb_calc_lines_device: same with a DEVICE buffer and an optional CUstream /
+ *   cudaStream_t (as void*, 0 = default stream); no host copy, asynchronous.
+ */
+int mmb_init_frame(mmb_invocation *inv, int frame, float t);
+int mmb_calc_lines(mmb_invocation *inv, int first_row, int last_row, void *q, int floatmap);
+int mmb_calc_lines_device(mmb_invocation *inv, int first_row, int last_row, void *device_q, int floatmap, void *stream);
+/* Batched entry for frame sharding: renders n frames (frame numbers
+ * and t values given) into consecutive W*H*bpp device buffers starting at device_q. */
+int mmb_render_frames_device(mmb_invocation *inv, int n, const int *frames, const float *ts, void *device_q, void *stream);
+int mmb_synchronize(mmb_invocation *inv);
+/* number of kernels launched by this invocation so far (bench accounting) */
+long mmb_launch_count(const mmb_invocation *inv);
+/* name of the most recently launched pixel kernel (for profiler filters) */
+const char *mmb_kernel_name(const mmb_invocation *inv);
+
+/* ---- native filters, callable directly (native-filters/native-filters.h) -----
+ * Gaussian blur of a device float4 image, sigma in pixels (gauss.c:643-670 chooses
+ * IIR for sigma >= 0.5 in both axes, the run-length FIR otherwise). */
+int mmb_gaussian_blur_device(int device, const float *device_in, float *device_out, int width, int height, float sigma_h_px,
+                             float sigma_v_px, void *stream);
+
+const char *mmb_last_error(void);
+const char *mmb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -88,6 +88,7 @@ struct Module {
 
 void register_all_builtins(Module &m);  // builtins.cpp
 
+void register_native_filters(Module &m);
 // Parses `source` into `m` (filters, main filter).  Throws CompileError.
 void parse_module(Module &m, const std::string &source);
 

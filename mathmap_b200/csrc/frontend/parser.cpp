@@ -816,8 +816,9 @@ class Parser {
 
 }  // namespace
 
-void parse_module(Module &m, const std::string &source) {
+void register_native_filters(Module &m) {
     // native filters are registered before the user's filters: mathmap_common.c:346-377
+    if (!m.filters.empty()) return;
     auto add_native = [&](const char *name, const char *func, std::vector<UservalInfo> uvs) {
         auto f = std::make_unique<Filter>();
         f->kind = FILTER_NATIVE;
@@ -833,13 +834,15 @@ void parse_module(Module &m, const std::string &source) {
         UservalInfo u; u.name = n; u.type = UV_FLOAT; u.float_min = lo; u.float_max = hi; u.float_default = d; return u;
     };
     auto bl = [](const char *n, int d) { UservalInfo u; u.name = n; u.type = UV_BOOL; u.bool_default = d; return u; };
-    if (m.filters.empty()) {
-        add_native("gaussian_blur", "native_filter_gaussian_blur",
-                   {img("in"), flt("horizontal_std_dev", 0.f, 2.f, 0.01f), flt("vertical_std_dev", 0.f, 2.f, 0.01f)});
-        add_native("convolve", "native_filter_convolve", {img("in"), img("kernel"), bl("normalize", 1), bl("copy_alpha", 1)});
-        add_native("half_convolve", "native_filter_half_convolve", {img("in"), img("mask"), bl("copy_alpha", 1)});
-        add_native("visualize_fft", "native_filter_visualize_fft", {img("in"), bl("ignore_alpha", 1)});
-    }
+    add_native("gaussian_blur", "native_filter_gaussian_blur",
+               {img("in"), flt("horizontal_std_dev", 0.f, 2.f, 0.01f), flt("vertical_std_dev", 0.f, 2.f, 0.01f)});
+    add_native("convolve", "native_filter_convolve", {img("in"), img("kernel"), bl("normalize", 1), bl("copy_alpha", 1)});
+    add_native("half_convolve", "native_filter_half_convolve", {img("in"), img("mask"), bl("copy_alpha", 1)});
+    add_native("visualize_fft", "native_filter_visualize_fft", {img("in"), bl("ignore_alpha", 1)});
+}
+
+void parse_module(Module &m, const std::string &source) {
+    register_native_filters(m);
     Parser p(m, source);
     // the __origVal macros (macros.c:191-194) need the parser to build trees
     m.register_macro("__origVal", "rgba:4 <- xy:2, image:1", [&p](std::vector<Expr *> &a) { return p.macro_orig_val_image(a, false); });

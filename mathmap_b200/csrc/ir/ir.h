@@ -102,7 +102,8 @@ struct Value {
     Stmt *def = nullptr;
     std::vector<Stmt *> uses;
     int const_bits = CONST_NONE;  // filled by analyze_constants
-    bool hoisted = false;         // evaluated once per frame on the host
+    bool hoisted = false;         // level == 0: evaluated once per frame on the host
+    int level = 3;                // 0 frame, 1 row, 3 pixel (see analyze_constants)
 };
 
 struct Const {
@@ -156,7 +157,7 @@ struct Stmt {
     Stmt *entry = nullptr, *body = nullptr;
     Stmt *parent = nullptr;
     Stmt *next = nullptr;
-    bool hoisted = false;  // control statement replayed on the host
+    int level = 3;  // if: level of the condition; while: level the whole loop runs at
 };
 
 // ---- filters (reference mathmap.h filter_t, userval.h userval_info_t) ----
@@ -258,7 +259,8 @@ Type rhs_type(const Rhs *rhs);
 int tuple_length_of_rhs(const Rhs *rhs);  // 0 if not a tuple producer
 
 std::string format_float(float f);  // round-trippable text of a float32
-std::string dump_ir(const FilterCode &code);
+std::string dump_ir(const FilterCode &code);  // one (filter ...) form
+std::string dump_module_ir(const std::vector<const FilterCode *> &codes, const std::string &main_name);
 std::string primary_to_string(const Primary &p);
 
 }  // namespace mm

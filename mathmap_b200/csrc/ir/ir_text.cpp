@@ -8,12 +8,14 @@
 //     (uservals (int "name" MIN MAX DEFAULT) (image "in" FLAGS) ...)
 //     (vars (ID TYPE [TUPLELEN]) ...)
 //     (code STMT ...)))
-//   STMT := (assign %cv.idx CONSTBITS HOISTED RHS)
-//         | (if RHS HOISTED (STMT ...) (STMT ...) (phis (phi %lhs CONSTBITS HOISTED RHS RHS2) ...))
-//         | (while (phis ...) RHS HOISTED (STMT ...))
+//   STMT := (assign %cv.idx CONSTBITS LEVEL RHS)
+//         | (if RHS LEVEL (STMT ...) (STMT ...) (phis (phi %lhs CONSTBITS LEVEL RHS RHS2) ...))
+//         | (while (phis ...) RHS LEVEL (STMT ...))
+//   LEVEL: 0 once per frame (host), 1 once per row, 3 per pixel
 //   RHS  := PRIM | (internal NAME) | (op NAME PRIM ...) | (tuple PRIM ...)
 //         | (closure FILTERNAME PRIM ...) | (filter FILTERNAME PRIM ...)
 //   PRIM := %cv.idx | %cv.u (never assigned: reads 0) | i:INT | f:FLOAT | c:RE,IM | k:UINT
+#include <set>
 #include <sstream>
 
 #include "ir.h"
@@ -39,7 +41,7 @@ static void dump_phis(std::ostringstream &o, const Stmt *p, int ind) {
     for (; p; p = p->next) {
         if (p->kind != ST_PHI) continue;
         o << "\n" << std::string(ind + 1, ' ') << "(phi " << primary_to_string(Primary::of(p->lhs)) << " " << p->lhs->const_bits << " "
-          << (p->lhs->hoisted ? 1 : 0) << " ";
+          << p->lhs->level << " ";
         dump_rhs(o, p->rhs);
         o << " ";
         dump_rhs(o, p->rhs2);
@@ -54,7 +56,7 @@ static void dump_stmts(std::ostringstream &o, const Stmt *s, int ind) {
         switch (s->kind) {
         case ST_NIL: break;
         case ST_ASSIGN:
-            o << pad << "(assign " << primary_to_string(Primary::of(s->lhs)) << " " << s->lhs->const_bits << " " << (s->lhs->hoisted ? 1 : 0) << " ";
+            o << pad << "(assign " << primary_to_string(Primary::of(s->lhs)) << " " << s->lhs->const_bits << " " << s->lhs->level << " ";
             dump_rhs(o, s->rhs);
             o << ")\n";
             break;
@@ -62,7 +64,7 @@ static void dump_stmts(std::ostringstream &o, const Stmt *s, int ind) {
         case ST_IF:
             o << pad << "(if ";
             dump_rhs(o, s->cond);
-            o << " " << (s->hoisted ? 1 : 0) << "\n" << pad << " (\n";
+            o << " " << s->level << "\n" << pad << " (\n";
             dump_stmts(o, s->cons, ind + 2);
             o << pad << " )\n" << pad << " (\n";
             dump_stmts(o, s->alt, ind + 2);
@@ -75,10 +77,25 @@ static void dump_stmts(std::ostringstream &o, const Stmt *s, int ind) {
             dump_phis(o, s->entry, ind + 1);
             o << "\n" << pad << " ";
             dump_rhs(o, s->cond);
-            o << " " << (s->hoisted ? 1 : 0) << "\n" << pad << " (\n";
+            o << " " << s->level << "\n" << pad << " (\n";
             dump_stmts(o, s->body, ind + 2);
             o << pad << " ))\n";
             break;
+        }
+    }
+}
+
+static void collect_compvars(const Stmt *s, std::set<const CompVar *> &out) {
+    auto rhs = [&](const Rhs *r) {
+        if (r) for_each_value_in_rhs(const_cast<Rhs *>(r), [&](Value *v) { out.insert(v->cv); });
+    };
+    for (; s; s = s->next) {
+        switch (s->kind) {
+        case ST_PHI: rhs(s->rhs2);  // fallthrough
+        case ST_ASSIGN: rhs(s->rhs); out.insert(s->lhs->cv); break;
+        case ST_IF: rhs(s->cond); collect_compvars(s->cons, out); collect_compvars(s->alt, out); collect_compvars(s->exit, out); break;
+        case ST_WHILE: rhs(s->cond); collect_compvars(s->entry, out); collect_compvars(s->body, out); break;
+        default: break;
         }
     }
 }
@@ -96,7 +113,7 @@ static std::string quote(const std::string &s) {
 std::string dump_ir(const FilterCode &code) {
     std::ostringstream o;
     const Filter *f = code.filter;
-    o << "(mmir 1\n (filter " << f->name << " (flags";
+    o << " (filter " << f->name << " (flags";
     if (f->flags & IMAGE_FLAG_UNIT) o << " unit";
     if (f->flags & IMAGE_FLAG_SQUARE) o << " square";
     o << ")\n  (uservals";
@@ -112,19 +129,26 @@ std::string dump_ir(const FilterCode &code) {
         o << ")";
     }
     o << ")\n  (vars";
+    std::set<const CompVar *> live;
+    collect_compvars(code.first, live);
     for (auto &cv : code.compvars) {
-        bool used = false;
-        for (Value *v : cv.values)
-            if (v->def || !v->uses.empty()) used = true;
-        if (!used) continue;
+        if (!live.count(&cv)) continue;
         o << "\n   (" << cv.id << " " << type_name(cv.type);
         if (cv.type == T_TUPLE) o << " " << cv.tuple_len;
         o << ")";
     }
     o << ")\n  (code\n";
     dump_stmts(o, code.first, 3);
-    o << "  )))\n";
+    o << "  ))\n";
     return o.str();
+}
+
+std::string dump_module_ir(const std::vector<const FilterCode *> &codes, const std::string &main_name) {
+    std::string s = "(mmir 1\n";
+    for (const FilterCode *c : codes)
+        if (c) s += dump_ir(*c);
+    s += " (main " + main_name + "))\n";
+    return s;
 }
 
 }  // namespace mm

@@ -689,56 +689,85 @@ void analyze_constants(FilterCode &code) {
         go(code.first, CONST_ALL);
     }
 
-    // hoisting: frame-constant values whose whole definition the host can replay
-    const int XY = CONST_X | CONST_Y;
-    bool ch = true;
-    for (auto &v : code.values) v.hoisted = false;
-    auto prim_hoisted = [&](const P &p) { return p.is_const || p.value->index < 0 || p.value->hoisted; };
-    auto rhs_hoistable = [&](const Rhs *r) {
-        if (!host_can_eval(r)) return false;
-        bool ok = true;
-        if (r->kind == RHS_PRIMARY) ok = prim_hoisted(r->prim);
+    // ---- evaluation levels ------------------------------------------------
+    // 0: once per frame, replayed on the host (reference: init_frame / xy_vars)
+    // 1: once per output row (reference: the "x-const" row locals)
+    // 3: every pixel
+    // A definition's level is the max of its own base level (from const bits and
+    // whether the host can evaluate it) and its arguments' levels.  Pure
+    // definitions may sit at a lower level than the control structure around
+    // them (they are speculated); phis are bound to their controlling condition;
+    // a loop runs at the max level of everything inside it.
+    for (auto &v : code.values) v.level = 0;
+    auto prim_level = [&](const P &p) { return (p.is_const || p.value->index < 0) ? 0 : p.value->level; };
+    auto rhs_level = [&](const Rhs *r) {
+        int l = 0;
+        if (r->kind == RHS_PRIMARY) l = prim_level(r->prim);
         else if (r->kind != RHS_INTERNAL)
-            for (auto &a : r->args) ok = ok && prim_hoisted(a);
-        return ok;
+            for (auto &a : r->args) l = std::max(l, prim_level(a));
+        return l;
     };
-    // optimistic start: every xy-const value with a host-evaluable definition
-    for (auto &v : code.values)
-        if (v.index >= 0 && v.def && (v.const_bits & XY) == XY) v.hoisted = true;
+    auto base_level = [&](const Value *v, const Rhs *r) {
+        int l = 3;
+        if ((v->const_bits & (CONST_X | CONST_Y)) == (CONST_X | CONST_Y)) l = 0;
+        else if (v->const_bits & CONST_X) l = 1;
+        if (l == 0 && !host_can_eval(r)) l = 1;
+        if (r->kind == RHS_OP && !r->op->pure) l = 3;
+        if (r->kind == RHS_FILTER) l = 3;
+        return l;
+    };
+    bool ch = true;
+    auto raise = [&](Value *v, int l) { if (l > v->level) { v->level = l; ch = true; } };
+    std::function<int(Stmt *)> lv = [&](Stmt *s) {
+        int mx = 0;  // max level of anything in this list
+        for (; s; s = s->next) {
+            switch (s->kind) {
+            case ST_ASSIGN:
+                raise(s->lhs, std::max(base_level(s->lhs, s->rhs), rhs_level(s->rhs)));
+                mx = std::max(mx, s->lhs->level);
+                break;
+            case ST_IF: {
+                int cl = rhs_level(s->cond);
+                if (!host_can_eval(s->cond)) cl = std::max(cl, 1);
+                s->level = cl;
+                mx = std::max(mx, std::max(lv(s->cons), lv(s->alt)));
+                for (Stmt *p = s->exit; p; p = p->next) {
+                    if (p->kind != ST_PHI) continue;
+                    raise(p->lhs, std::max(cl, std::max(rhs_level(p->rhs), rhs_level(p->rhs2))));
+                    mx = std::max(mx, p->lhs->level);
+                }
+                break;
+            }
+            case ST_WHILE: {
+                int ll = std::max(s->level, rhs_level(s->cond));
+                if (!host_can_eval(s->cond)) ll = std::max(ll, 1);
+                for (Stmt *p = s->entry; p; p = p->next)
+                    if (p->kind == ST_PHI) ll = std::max(ll, std::max(p->lhs->level, std::max(rhs_level(p->rhs), rhs_level(p->rhs2))));
+                ll = std::max(ll, lv(s->body));
+                for (Stmt *p = s->entry; p; p = p->next)
+                    if (p->kind == ST_PHI) raise(p->lhs, ll);
+                if (ll != s->level) { s->level = ll; ch = true; }
+                mx = std::max(mx, ll);
+                break;
+            }
+            default: break;
+            }
+        }
+        return mx;
+    };
+    std::function<void(Stmt *)> reset = [&](Stmt *s) {
+        for (; s; s = s->next) {
+            s->level = 0;
+            if (s->kind == ST_IF) { reset(s->cons); reset(s->alt); }
+            if (s->kind == ST_WHILE) reset(s->body);
+        }
+    };
+    reset(code.first);
     while (ch) {
         ch = false;
-        std::function<void(Stmt *)> hz = [&](Stmt *s) {
-            for (; s; s = s->next) {
-                switch (s->kind) {
-                case ST_ASSIGN:
-                    if (s->lhs->hoisted && !rhs_hoistable(s->rhs)) { s->lhs->hoisted = false; ch = true; }
-                    break;
-                case ST_IF: {
-                    bool c = rhs_hoistable(s->cond);
-                    hz(s->cons);
-                    hz(s->alt);
-                    for (Stmt *p = s->exit; p; p = p->next)
-                        if (p->kind == ST_PHI && p->lhs->hoisted && !(c && rhs_hoistable(p->rhs) && rhs_hoistable(p->rhs2))) { p->lhs->hoisted = false; ch = true; }
-                    s->hoisted = c;
-                    break;
-                }
-                case ST_WHILE: {
-                    bool c = rhs_hoistable(s->cond);
-                    // a loop is replayed on the host only if all of its phis are hoisted
-                    for (Stmt *p = s->entry; p; p = p->next)
-                        if (p->kind == ST_PHI && !(p->lhs->hoisted && rhs_hoistable(p->rhs) && rhs_hoistable(p->rhs2))) c = false;
-                    for (Stmt *p = s->entry; p; p = p->next)
-                        if (p->kind == ST_PHI && p->lhs->hoisted && !c) { p->lhs->hoisted = false; ch = true; }
-                    hz(s->body);
-                    s->hoisted = c;
-                    break;
-                }
-                default: break;
-                }
-            }
-        };
-        hz(code.first);
+        lv(code.first);
     }
+    for (auto &v : code.values) v.hoisted = v.level == 0;
 }
 
 std::unique_ptr<FilterCode> compile_filter(Module &mod, Filter *filter, bool optimize) {

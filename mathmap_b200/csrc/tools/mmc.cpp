@@ -17,11 +17,14 @@ int main(int argc, char **argv) {
     try {
         mm::Module m;
         mm::parse_module(m, ss.str());
+        std::vector<std::unique_ptr<mm::FilterCode>> codes;
+        std::vector<const mm::FilterCode *> ptrs;
         for (auto &f : m.filters) {
             if (f->kind != mm::FILTER_MATHMAP) continue;
-            auto code = mm::compile_filter(m, f.get(), opt);
-            std::cout << mm::dump_ir(*code);
+            codes.push_back(mm::compile_filter(m, f.get(), opt));
+            ptrs.push_back(codes.back().get());
         }
+        std::cout << mm::dump_module_ir(ptrs, m.main_filter->name);
     } catch (mm::CompileError &e) {
         fprintf(stderr, "%s:%d:%d: %s\n", argv[1], e.line + 1, e.column + 1, e.message.c_str());
         return 1;
