@@ -1,0 +1,444 @@
+#include "cuda_emit.h"
+
+#include <cmath>
+#include <cstring>
+#include <set>
+#include <sstream>
+
+namespace mmbackend {
+
+using namespace mm;
+
+namespace {
+
+[[noreturn]] void unsupported(const std::string &what) {
+    CompileError e;
+    e.message = "CUDA backend: " + what;
+    throw e;
+}
+
+std::string sanitize(const std::string &s) {
+    std::string r;
+    for (char c : s) r += (isalnum((unsigned char)c) || c == '_') ? c : '_';
+    return r;
+}
+
+std::string float_literal(float f) {
+    if (std::isnan(f)) return "__int_as_float(0x7fc00000)";
+    if (std::isinf(f)) return f > 0 ? "__int_as_float(0x7f800000)" : "__int_as_float(0xff800000)";
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.9g", (double)f);
+    std::string s = buf;
+    if (!strpbrk(buf, ".en")) s += ".0";
+    return s + "f";
+}
+
+struct Emitter {
+    const mmb_module &mod;
+    const FilterCode &code;
+    bool call_flavour;  // true: a __device__ function evaluating everything per call (non-inlined filter calls)
+    std::ostringstream out;
+    std::set<const Value *> uniform_set;
+    std::vector<const Value *> uniform_order;
+    std::set<const Filter *> &called;  // filters reached through RHS_FILTER
+
+    Emitter(const mmb_module &m, const FilterCode &c, bool cf, std::set<const Filter *> &cl) : mod(m), code(c), call_flavour(cf), called(cl) {}
+
+    bool on_device(int level) const { return call_flavour || level >= 1; }
+
+    static std::string vname(const Value *v) { return "v" + std::to_string(v->cv->id) + "_" + std::to_string(v->index); }
+    static std::string ctype(const CompVar *cv) {
+        switch (cv->type) {
+        case T_INT: case T_NIL: return "int";
+        case T_FLOAT: return "float";
+        case T_COMPLEX: return "float2";
+        case T_COLOR: return "mm_color";
+        case T_CURVE: return "const float *";
+        case T_GRADIENT: return "const mm_color *";
+        case T_IMAGE: return "int";
+        case T_TUPLE: return "mm_tup<" + std::to_string(std::max(1, cv->tuple_len)) + ">";
+        default: unsupported("tree vectors (computed tuple subscripts)");
+        }
+    }
+
+    std::string prim(const Primary &p) {
+        if (p.is_const) {
+            switch (p.c.type) {
+            case T_INT: return p.c.i < 0 ? "(" + std::to_string(p.c.i) + ")" : std::to_string(p.c.i);
+            case T_FLOAT: { std::string s = float_literal(p.c.f); return p.c.f < 0 ? "(" + s + ")" : s; }
+            case T_COMPLEX: return "make_float2(" + float_literal(p.c.c.real()) + ", " + float_literal(p.c.c.imag()) + ")";
+            case T_COLOR: return std::to_string(p.c.color) + "u";
+            default: unsupported("constant of non-scalar type");
+            }
+        }
+        const Value *v = p.value;
+        if (v->index < 0) return v->cv->type == T_TUPLE ? ctype(v->cv) + "{}" : (v->cv->type == T_COMPLEX ? "make_float2(0.f, 0.f)" : "0");
+        if (!on_device(v->level)) {
+            if (uniform_set.insert(v).second) uniform_order.push_back(v);
+            return "U." + vname(v);
+        }
+        return vname(v);
+    }
+    Type ptype(const Primary &p) const { return primary_type(p); }
+    std::string as_float(const Primary &p) {
+        std::string s = prim(p);
+        return ptype(p) == T_FLOAT ? s : "(float)" + s;
+    }
+    std::string as_complex(const Primary &p) {
+        if (ptype(p) == T_COMPLEX) return prim(p);
+        return "make_float2(" + as_float(p) + ", 0.f)";
+    }
+
+    std::string internal(const std::string &n) {
+        if (n == "x" || n == "y" || n == "t" || n == "frame") return n;
+        if (n == "R") return "P.R";
+        if (n == "__canvasPixelW") return "P.img_w";
+        if (n == "__canvasPixelH") return "P.img_h";
+        if (n == "__renderPixelW") return "P.render_w";
+        if (n == "__renderPixelH") return "P.render_h";
+        unsupported("internal " + n + " is not available on the device");
+    }
+
+    std::string userval_access(int op, const Primary &idx) {
+        if (!call_flavour) unsupported("userval access outside the frame-constant slice");
+        (void)op;
+        return "a" + std::to_string(idx.c.i);
+    }
+
+    std::string op_expr(const Rhs *r, Type result_type) {
+        const OpInfo *op = r->op;
+        auto A = [&](int i) { return prim(r->args[i]); };
+        auto F = [&](int i) { return as_float(r->args[i]); };
+        auto Z = [&](int i) { return as_complex(r->args[i]); };
+        Type mx = T_INT;
+        for (auto &a : r->args) mx = std::max(mx, ptype(a));
+        auto arith = [&](const char *sym, const char *cfn) {
+            if (mx == T_COMPLEX) return std::string(cfn) + "(" + Z(0) + ", " + Z(1) + ")";
+            return "(" + A(0) + " " + sym + " " + A(1) + ")";
+        };
+        auto fn1 = [&](const char *name) { return std::string(name) + "(" + F(0) + ")"; };
+        auto fn2 = [&](const char *name) { return std::string(name) + "(" + F(0) + ", " + F(1) + ")"; };
+        auto cfn1 = [&](const char *name) { return std::string(name) + "(" + Z(0) + ")"; };
+        switch (op->id) {
+        case OP_NOP: return "0";
+        case OP_INT2FLOAT: return "(float)" + A(0);
+        case OP_FLOAT2INT: return "mm_f2i(" + F(0) + ")";
+        case OP_INT2COMPLEX: case OP_FLOAT2COMPLEX: return Z(0);
+        case OP_ADD: return arith("+", "mm_cadd");
+        case OP_SUB: return arith("-", "mm_csub");
+        case OP_MUL: return arith("*", "mm_cmul");
+        case OP_NEG: return mx == T_COMPLEX ? "mm_cneg(" + Z(0) + ")" : "(-" + A(0) + ")";
+        case OP_DIV: return fn2("mm_div");
+        case OP_MOD: return fn2("mm_mod");
+        case OP_ABS: return mx == T_INT ? "mm_abs(" + A(0) + ")" : "mm_abs(" + F(0) + ")";
+        case OP_MIN: return mx == T_INT ? "mm_min(" + A(0) + ", " + A(1) + ")" : fn2("mm_min");
+        case OP_MAX: return mx == T_INT ? "mm_max(" + A(0) + ", " + A(1) + ")" : fn2("mm_max");
+        case OP_SQRT: return fn1("mm_sqrt");
+        case OP_HYPOT: return fn2("mm_hypot");
+        case OP_SIN: return fn1("mm_sin");
+        case OP_COS: return fn1("mm_cos");
+        case OP_TAN: return fn1("mm_tan");
+        case OP_ASIN: return fn1("mm_asin");
+        case OP_ACOS: return fn1("mm_acos");
+        case OP_ATAN: return fn1("mm_atan");
+        case OP_ATAN2: return fn2("mm_atan2");
+        case OP_POW: return fn2("mm_pow");
+        case OP_EXP: return fn1("mm_exp");
+        case OP_LOG: return fn1("mm_log");
+        case OP_SINH: return fn1("mm_sinh");
+        case OP_COSH: return fn1("mm_cosh");
+        case OP_TANH: return fn1("mm_tanh");
+        case OP_ASINH: return fn1("mm_asinh");
+        case OP_ACOSH: return fn1("mm_acosh");
+        case OP_ATANH: return fn1("mm_atanh");
+        case OP_GAMMA: return fn1("mm_gamma");
+        case OP_BETA: return fn2("mm_beta");
+        case OP_FLOOR: return fn1("mm_floor");
+        case OP_CEIL: return fn1("mm_ceil");
+        case OP_EQ: return "(" + A(0) + " == " + A(1) + ")";
+        case OP_LESS: return "(" + A(0) + " < " + A(1) + ")";
+        case OP_LEQ: return "(" + A(0) + " <= " + A(1) + ")";
+        case OP_NOT: return "(!" + A(0) + ")";
+        case OP_PRINT: case OP_NEWLINE: case OP_START_DEBUG_TUPLE: case OP_SET_DEBUG_TUPLE_DATA: return "0";
+        case OP_APPLY_CURVE: return "mm_apply_curve(" + A(0) + ", " + F(1) + ")";
+        case OP_APPLY_GRADIENT: return "mm_apply_gradient(" + A(0) + ", " + F(1) + ")";
+        case OP_ORIG_VAL: return "mm_orig_val(P, " + A(2) + ", " + F(0) + ", " + F(1) + ", " + F(3) + ")";
+        case OP_IMAGE_PIXEL_WIDTH: return "P.images[" + A(0) + "].w";
+        case OP_IMAGE_PIXEL_HEIGHT: return "P.images[" + A(0) + "].h";
+        case OP_MAKE_RGBA_COLOR: return "mm_make_color(" + F(0) + ", " + F(1) + ", " + F(2) + ", " + F(3) + ")";
+        case OP_RED: return "mm_red(" + A(0) + ")";
+        case OP_GREEN: return "mm_green(" + A(0) + ")";
+        case OP_BLUE: return "mm_blue(" + A(0) + ")";
+        case OP_ALPHA: return "mm_alpha(" + A(0) + ")";
+        case OP_TUPLE_NTH: return A(0) + ".v[" + A(1) + "]";
+        case OP_COMPLEX: return "mm_complex(" + F(0) + ", " + F(1) + ")";
+        case OP_C_REAL: return Z(0) + ".x";
+        case OP_C_IMAG: return Z(0) + ".y";
+        case OP_C_SQRT: return cfn1("mm_csqrt");
+        case OP_C_SIN: return cfn1("mm_csin");
+        case OP_C_COS: return cfn1("mm_ccos");
+        case OP_C_TAN: return cfn1("mm_ctan");
+        case OP_C_ASIN: return cfn1("mm_casin");
+        case OP_C_ACOS: return cfn1("mm_cacos");
+        case OP_C_ATAN: return cfn1("mm_catan");
+        case OP_C_POW: return "mm_cpow(" + Z(0) + ", " + Z(1) + ")";
+        case OP_C_EXP: return cfn1("mm_cexp");
+        case OP_C_LOG: return cfn1("mm_clog");
+        case OP_C_ARG: return cfn1("mm_carg");
+        case OP_C_SINH: return cfn1("mm_csinh");
+        case OP_C_COSH: return cfn1("mm_ccosh");
+        case OP_C_TANH: return cfn1("mm_ctanh");
+        case OP_C_ASINH: return cfn1("mm_casinh");
+        case OP_C_ACOSH: return cfn1("mm_cacosh");
+        case OP_C_ATANH: return cfn1("mm_catanh");
+        case OP_C_GAMMA: return cfn1("mm_cgamma");
+        case OP_LIBNOISE_PERLIN: return "mm_libnoise_perlin(" + A(0) + ", " + F(1) + ", " + F(2) + ", " + F(3) + ", " + F(4) + ", " + F(5) + ")";
+        case OP_LIBNOISE_BILLOW: return "mm_libnoise_billow(" + A(0) + ", " + F(1) + ", " + F(2) + ", " + F(3) + ", " + F(4) + ", " + F(5) + ")";
+        case OP_LIBNOISE_RIDGED_MULTI: return "mm_libnoise_ridged_multi(" + A(0) + ", " + F(1) + ", " + F(2) + ", " + F(3) + ", " + F(4) + ")";
+        case OP_LIBNOISE_VORONOI: return "mm_libnoise_voronoi(" + F(0) + ", " + F(1) + ", " + F(2) + ", " + F(3) + ")";
+        case OP_USERVAL_INT: case OP_USERVAL_FLOAT: case OP_USERVAL_BOOL: case OP_USERVAL_COLOR:
+        case OP_USERVAL_CURVE: case OP_USERVAL_GRADIENT: case OP_USERVAL_IMAGE:
+            return userval_access(op->id, r->args[0]);
+        case OP_OUTPUT_TUPLE: return "(mm_ret = " + A(0) + ", 0)";
+        case OP_STRIP_RESIZE: return A(0);  // device image handles never carry a resize wrapper of their own
+        default:
+            (void)result_type;
+            unsupported(std::string("op ") + op->name + " cannot run per pixel on the device (it needs the host or an absent third-party library)");
+        }
+    }
+
+    std::string rhs_expr(const Rhs *r, const CompVar *dest) {
+        switch (r->kind) {
+        case RHS_PRIMARY: return prim(r->prim);
+        case RHS_INTERNAL: return internal(r->internal);
+        case RHS_OP: return op_expr(r, dest ? dest->type : T_INT);
+        case RHS_TUPLE: {
+            std::string s = "mm_tup<" + std::to_string(dest ? std::max(1, dest->tuple_len) : (int)r->args.size()) + ">{{";
+            for (size_t i = 0; i < r->args.size(); ++i) s += (i ? ", " : "") + as_float(r->args[i]);
+            return s + "}}";
+        }
+        case RHS_FILTER: {
+            const Filter *callee = r->filter;
+            called.insert(callee);
+            size_t nuv = callee->uservals.size();
+            std::string s = "mm_call_" + sanitize(callee->name) + "(P";
+            for (size_t i = 0; i < nuv; ++i) {
+                int t = callee->uservals[i].type;
+                s += ", " + ((t == UV_FLOAT) ? as_float(r->args[i]) : prim(r->args[i]));
+            }
+            s += ", " + as_float(r->args[nuv]) + ", " + as_float(r->args[nuv + 1]) + ", " + as_float(r->args[nuv + 2]) + ")";
+            return s;
+        }
+        case RHS_CLOSURE: unsupported("an image closure that is not frame-constant");
+        default: unsupported("tree vectors (computed tuple subscripts)");
+        }
+    }
+
+    // does this statement list contain anything evaluated on the device?
+    bool has_device(const Stmt *s) const {
+        for (; s; s = s->next) {
+            switch (s->kind) {
+            case ST_ASSIGN: case ST_PHI: if (on_device(s->lhs->level)) return true; break;
+            case ST_IF: if (has_device(s->cons) || has_device(s->alt) || has_device(s->exit)) return true; break;
+            case ST_WHILE: if (on_device(s->level)) return true; if (has_device(s->body)) return true; break;
+            default: break;
+            }
+        }
+        return false;
+    }
+
+    void emit_phis(const Stmt *phis, int branch, const std::string &ind) {
+        std::vector<const Stmt *> live;
+        for (const Stmt *p = phis; p; p = p->next)
+            if (p->kind == ST_PHI && on_device(p->lhs->level)) {
+                const Rhs *src = branch == 0 ? p->rhs : p->rhs2;
+                if (src->kind == RHS_PRIMARY && !src->prim.is_const && src->prim.value == p->lhs) continue;
+                live.push_back(p);
+            }
+        // parallel-copy hazard: a source that is the destination of another copy in this set
+        bool hazard = false;
+        for (const Stmt *p : live) {
+            const Rhs *src = branch == 0 ? p->rhs : p->rhs2;
+            if (src->kind == RHS_PRIMARY && !src->prim.is_const)
+                for (const Stmt *q : live)
+                    if (q != p && q->lhs == src->prim.value) hazard = true;
+        }
+        if (!hazard) {
+            for (const Stmt *p : live) out << ind << vname(p->lhs) << " = " << rhs_expr(branch == 0 ? p->rhs : p->rhs2, p->lhs->cv) << ";\n";
+            return;
+        }
+        out << ind << "{\n";
+        int k = 0;
+        for (const Stmt *p : live) out << ind << "    " << ctype(p->lhs->cv) << " mm_pc" << k++ << " = " << rhs_expr(branch == 0 ? p->rhs : p->rhs2, p->lhs->cv) << ";\n";
+        k = 0;
+        for (const Stmt *p : live) out << ind << "    " << vname(p->lhs) << " = mm_pc" << k++ << ";\n";
+        out << ind << "}\n";
+    }
+
+    void emit_stmts(const Stmt *s, const std::string &ind) {
+        for (; s; s = s->next) {
+            switch (s->kind) {
+            case ST_ASSIGN:
+                if (on_device(s->lhs->level)) out << ind << vname(s->lhs) << " = " << rhs_expr(s->rhs, s->lhs->cv) << ";\n";
+                break;
+            case ST_IF:
+                if (!(has_device(s->cons) || has_device(s->alt) || has_device(s->exit))) break;
+                out << ind << "if (" << rhs_expr(s->cond, nullptr) << ") {\n";
+                emit_stmts(s->cons, ind + "    ");
+                emit_phis(s->exit, 0, ind + "    ");
+                out << ind << "} else {\n";
+                emit_stmts(s->alt, ind + "    ");
+                emit_phis(s->exit, 1, ind + "    ");
+                out << ind << "}\n";
+                break;
+            case ST_WHILE:
+                if (!on_device(s->level)) break;  // replayed on the host; nothing inside is per-pixel
+                emit_phis(s->entry, 0, ind);
+                out << ind << "while (" << rhs_expr(s->cond, nullptr) << ") {\n";
+                emit_stmts(s->body, ind + "    ");
+                emit_phis(s->entry, 1, ind + "    ");
+                out << ind << "}\n";
+                break;
+            default: break;
+            }
+        }
+    }
+
+    void collect_decls(const Stmt *s, std::vector<const Value *> &vals) const {
+        for (; s; s = s->next) {
+            switch (s->kind) {
+            case ST_ASSIGN: case ST_PHI: if (on_device(s->lhs->level)) vals.push_back(s->lhs); break;
+            case ST_IF: collect_decls(s->cons, vals); collect_decls(s->alt, vals); collect_decls(s->exit, vals); break;
+            case ST_WHILE: collect_decls(s->entry, vals); collect_decls(s->body, vals); break;
+            default: break;
+            }
+        }
+    }
+};
+
+size_t field_size(Type t, int tuple_len) {
+    switch (t) {
+    case T_COMPLEX: return 8;
+    case T_CURVE: case T_GRADIENT: return 8;
+    case T_TUPLE: return 4 * (size_t)std::max(1, tuple_len);
+    default: return 4;
+    }
+}
+
+}  // namespace
+
+CudaModuleSource emit_cuda_module(const mmb_module &m) {
+    CudaModuleSource src;
+    std::ostringstream text;
+    std::set<const Filter *> called, emitted_calls;
+    std::ostringstream kernels_text;
+
+    // forward declarations of callable filters are emitted once we know which are called
+    std::vector<std::string> bodies;
+    for (auto &fp : m.mod->filters) {
+        const Filter *f = fp.get();
+        if (f->kind != FILTER_MATHMAP) continue;
+        const FilterCode *code = m.code_for(f);
+        std::string name = sanitize(f->name);
+        Emitter e(m, *code, false, called);
+        // body first (discovers uniforms)
+        std::vector<const Value *> decls;
+        e.collect_decls(code->first, decls);
+        e.emit_stmts(code->first, "    ");
+        std::string body = e.out.str();
+
+        FilterKernel k;
+        k.filter = f;
+        k.kernel_name = "mm_kernel_" + name;
+        // layout: 8-byte fields first, then 4-byte ones
+        std::vector<const Value *> order = e.uniform_order;
+        std::stable_sort(order.begin(), order.end(), [](const Value *a, const Value *b) {
+            auto big = [](const Value *v) { return v->cv->type == T_CURVE || v->cv->type == T_GRADIENT || v->cv->type == T_COMPLEX; };
+            return big(a) && !big(b);
+        });
+        size_t off = 0;
+        std::ostringstream st;
+        st << "struct mm_uniforms_" << name << " {\n";
+        for (const Value *v : order) {
+            UniformField uf;
+            uf.value = v;
+            uf.type = v->cv->type;
+            uf.tuple_len = v->cv->tuple_len;
+            uf.size = field_size(uf.type, uf.tuple_len);
+            uf.offset = off;
+            off += uf.size;
+            k.uniforms.push_back(uf);
+            st << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
+        }
+        if (off == 0) { st << "    int mm_unused;\n"; off = 4; }
+        off = (off + 7) & ~(size_t)7;
+        st << "};\n";
+        k.uniforms_size = off;
+
+        std::ostringstream fn;
+        fn << st.str();
+        fn << "static __device__ __forceinline__ mm_tup<4> mm_eval_" << name << "(const mm_params &P, const mm_uniforms_" << name
+           << " &U, float x, float y, float t, int frame) {\n";
+        fn << "    mm_tup<4> mm_ret = mm_tup<4>{};\n";
+        for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
+        fn << body;
+        fn << "    return mm_ret;\n}\n";
+        fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H) " << k.kernel_name << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
+           << name << " U) {\n"
+           << "    int col, row;\n"
+           << "    mm_pixel_coords(col, row);\n"
+           << "    if (col >= P.region_w || row >= P.num_rows) return;\n"
+           << "    float x = __ldg(P.xs + (col + P.region_x));\n"
+           << "    float y = __ldg(P.ys + (row + P.first_row));\n"
+           << "    mm_tup<4> r = mm_eval_" << name << "(P, U, x, y, P.t, P.frame);\n"
+           << "    mm_store_pixel(P, row + P.first_row, col, r);\n"
+           << "}\n";
+        bodies.push_back(fn.str());
+        src.kernels[f] = k;
+    }
+
+    // device functions for filters that are called rather than inlined (recursion, colour arguments)
+    std::ostringstream calls, protos;
+    std::set<const Filter *> pending = called;
+    while (!pending.empty()) {
+        const Filter *f = *pending.begin();
+        pending.erase(pending.begin());
+        if (!emitted_calls.insert(f).second) continue;
+        const FilterCode *code = m.code_for(f);
+        std::string name = sanitize(f->name);
+        std::set<const Filter *> more;
+        Emitter e(m, *code, true, more);
+        std::vector<const Value *> decls;
+        e.collect_decls(code->first, decls);
+        e.emit_stmts(code->first, "    ");
+        std::ostringstream sig;
+        sig << "__device__ mm_tup<4> mm_call_" << name << "(const mm_params &P";
+        for (auto &u : f->uservals) {
+            const char *ct = "int";
+            switch (u.type) {
+            case UV_FLOAT: ct = "float"; break;
+            case UV_COLOR: ct = "mm_color"; break;
+            case UV_CURVE: ct = "const float *"; break;
+            case UV_GRADIENT: ct = "const mm_color *"; break;
+            default: break;
+            }
+            sig << ", " << ct << " a" << u.index;
+        }
+        sig << ", float x, float y, float t)";
+        protos << sig.str() << ";\n";
+        calls << sig.str() << " {\n    const int frame = 0;\n    (void)frame;\n    mm_tup<4> mm_ret = mm_tup<4>{};\n";
+        for (const Value *v : decls) calls << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
+        calls << e.out.str() << "    return mm_ret;\n}\n";
+        for (const Filter *g : more)
+            if (!emitted_calls.count(g)) pending.insert(g);
+    }
+
+    text << "// generated by mathmap_b200 backend/cuda_emit.cpp\n";
+    text << protos.str();
+    for (auto &b : bodies) text << b;
+    text << calls.str();
+    src.text = text.str();
+    return src;
+}
+
+}  // namespace mmbackend

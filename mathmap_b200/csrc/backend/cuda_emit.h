@@ -1,0 +1,38 @@
+// IR -> CUDA C.  The counterpart of the reference's IR -> C printer
+// (backends/cc.c:73-448) and per-filter skeleton (new_template.c.in), designed
+// for the GPU: plain statements instead of GNU statement expressions, tuples in
+// registers, no per-pixel heap, frame-constant values passed as a by-value
+// uniforms struct computed on the host, one pixel per thread.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../cabi_module.h"
+
+namespace mmbackend {
+
+struct UniformField {
+    const mm::Value *value;
+    mm::Type type;
+    int tuple_len;
+    size_t offset;
+    size_t size;
+};
+
+struct FilterKernel {
+    const mm::Filter *filter = nullptr;
+    std::string kernel_name;           // extern "C" __global__ entry
+    std::vector<UniformField> uniforms;
+    size_t uniforms_size = 0;          // sizeof(mm_uniforms_<f>) (>= 4)
+};
+
+struct CudaModuleSource {
+    std::string text;                                  // generated part (prepended with the runtime by the NVRTC driver)
+    std::map<const mm::Filter *, FilterKernel> kernels;  // every mathmap filter that can be rendered
+};
+
+// Throws mm::CompileError when the IR uses something the device cannot do.
+CudaModuleSource emit_cuda_module(const mmb_module &m);
+
+}  // namespace mmbackend

@@ -1,0 +1,923 @@
+// The render half of the C ABI: invocations, the per-frame host replay of
+// frame-constant IR (the reference's init_frame, new_template.c.in:314-337),
+// render_image / native filters as kernel launches, and calc_lines as one
+// pixel-grid launch per band (new_template.c.in:208-312).
+#include <cuda_runtime_api.h>
+
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+
+#include "../../../include/mathmap_b200.h"
+#include "../ir/eval.h"
+#include "../runtime/mm_types.h"
+#include "kernels.h"
+#include "nvrtc_module.h"
+
+using namespace mm;
+using namespace mmbackend;
+
+namespace mmbackend {
+long compile_only(mmb_module *m, const KernelConfig &cfg, std::string &err);
+}
+
+namespace {
+
+struct Fail {
+    std::string msg;
+};
+[[noreturn]] void fail(const std::string &m) { throw Fail{m}; }
+void ck(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) fail(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// Host-side value of a frame-constant IR value.
+struct HVal {
+    Type type = T_INT;
+    int i = 0;
+    float f = 0.f;
+    std::complex<float> c;
+    uint32_t color = 0;
+    int image = -1;             // index into Invocation::images
+    const void *ptr = nullptr;  // device pointer of a curve / gradient
+    std::vector<float> tuple;
+};
+
+enum ImageKind { IMG_DRAWABLE = 0, IMG_FLOATMAP = 1, IMG_CLOSURE = 2 };
+
+struct HostImage {
+    int kind = IMG_DRAWABLE;
+    void *data = nullptr;  // device
+    bool owned = false;
+    int w = 0, h = 0;
+    int num_frames = 1;
+    float sx = 0, sy = 0, mx = 1, my = 1;
+    float ax = 0, bx = 0, ay = 0, by = 0;
+    float xf = 1.f, yf = 1.f;
+    bool resized = false;
+    int original = -1;  // for resize wrappers: the wrapped image
+    const Filter *filter = nullptr;
+    std::vector<HVal> args;
+};
+
+struct Userval {
+    int type = UV_INT;
+    int i = 0;
+    float f = 0;
+    uint32_t color = 0;
+    void *table = nullptr;  // device curve/gradient
+    int image = -1;
+};
+
+struct FrameData {
+    std::vector<unsigned char> uniforms;
+    mm_image slots[MM_MAX_IMAGES];
+    int nslots = 0;
+};
+
+}  // namespace
+
+struct mmb_invocation {
+    mmb_module *m = nullptr;
+    std::shared_ptr<ModuleBackend> backend;
+    int device = 0;
+    int W = 0, H = 0;
+    KernelConfig cfg;
+    uint32_t edge_color_x = 0, edge_color_y = 0;
+    int bpp = 4;
+    cudaStream_t stream = nullptr;
+    std::vector<Userval> uservals;
+    std::vector<HostImage> images;
+    size_t persistent_images = 0;  // images [0, persistent) survive across frames
+    int frame = 0;
+    float t = 0.f;
+    bool frame_ready = false;
+    FrameData main_frame;
+    long launches = 0;
+    std::string kernel_name;
+    std::map<std::string, float *> coord_cache;
+    std::multimap<size_t, void *> free_blocks;              // device allocation pool
+    std::vector<std::pair<size_t, void *>> frame_blocks;    // blocks in use by the current frame
+    std::map<std::string, int> native_cache;                // per frame: key -> image index
+    void *staging = nullptr;
+    size_t staging_bytes = 0;
+    void *staging2 = nullptr;
+    size_t staging2_bytes = 0;
+    void *default_curve = nullptr, *default_gradient = nullptr;
+
+    void *alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        auto it = free_blocks.lower_bound(bytes);
+        if (it != free_blocks.end() && it->first <= bytes + bytes / 4) {
+            void *p = it->second;
+            size_t sz = it->first;
+            free_blocks.erase(it);
+            frame_blocks.push_back({sz, p});
+            return p;
+        }
+        void *p = nullptr;
+        ck(cudaMalloc(&p, bytes), "cudaMalloc");
+        frame_blocks.push_back({bytes, p});
+        return p;
+    }
+    void release_frame_blocks() {
+        for (auto &b : frame_blocks) free_blocks.insert(b);
+        frame_blocks.clear();
+    }
+    void *ensure_staging(void *&buf, size_t &cap, size_t bytes) {
+        if (cap < bytes) {
+            if (buf) cudaFree(buf);
+            buf = nullptr;
+            cap = 0;
+            ck(cudaMalloc(&buf, bytes), "cudaMalloc(staging)");
+            cap = bytes;
+        }
+        return buf;
+    }
+};
+
+namespace {
+
+// ------------------------------------------------------------ coordinate arrays
+// CALC_VIRTUAL_X / CALC_VIRTUAL_Y (opmacros.h:156-157) in double on the host,
+// narrowed to float, once per (size, offset); kernels read them instead of doing
+// double divisions per pixel.
+const float *coords(mmb_invocation *inv, bool is_y, int size, float offset, int count) {
+    char key[96];
+    snprintf(key, sizeof key, "%c%d_%a_%d", is_y ? 'y' : 'x', size, (double)offset, count);
+    auto it = inv->coord_cache.find(key);
+    if (it != inv->coord_cache.end()) return it->second;
+    std::vector<float> v(count);
+    for (int p = 0; p < count; ++p) {
+        if (is_y) v[p] = (float)((-(p) + ((size)-1) / 2.0 - (offset)) / (((size)-1) / 2.0));
+        else v[p] = (float)(((p) - ((size)-1) / 2.0 + (offset)) / (((size)-1) / 2.0));
+    }
+    float *d = nullptr;
+    ck(cudaMalloc((void **)&d, sizeof(float) * count), "cudaMalloc(coords)");
+    ck(cudaMemcpyAsync(d, v.data(), sizeof(float) * count, cudaMemcpyHostToDevice, inv->stream), "cudaMemcpy(coords)");
+    ck(cudaStreamSynchronize(inv->stream), "sync(coords)");
+    inv->coord_cache[key] = d;
+    return d;
+}
+
+mm_image to_device_desc(const HostImage &h) {
+    mm_image d;
+    memset(&d, 0, sizeof d);
+    d.data = h.data;
+    d.kind = h.kind == IMG_FLOATMAP ? MM_IMAGE_FLOATMAP : MM_IMAGE_DRAWABLE;
+    d.w = h.w; d.h = h.h; d.num_frames = h.num_frames;
+    d.sx = h.sx; d.sy = h.sy; d.mx = h.mx; d.my = h.my;
+    d.ax = h.ax; d.bx = h.bx; d.ay = h.ay; d.by = h.by;
+    d.xf = h.xf; d.yf = h.yf;
+    return d;
+}
+
+// -------------------------------------------------------------- host replay
+struct Replay {
+    mmb_invocation *inv;
+    const Filter *filter;
+    const FilterCode *code;
+    const std::vector<HVal> &uservals;  // of this filter instance
+    int frame;
+    float t;
+    int depth;
+    std::map<const Value *, HVal> env;
+
+    Replay(mmb_invocation *i, const Filter *f, const std::vector<HVal> &uv, int fr, float tt, int d)
+        : inv(i), filter(f), code(i->m->code_for(f)), uservals(uv), frame(fr), t(tt), depth(d) {}
+
+    static HVal from_const(const Const &c) {
+        HVal v;
+        v.type = c.type;
+        v.i = c.i; v.f = c.f; v.c = c.c; v.color = c.color;
+        return v;
+    }
+    static Const to_const(const HVal &v) {
+        Const c;
+        c.type = v.type;
+        c.i = v.i; c.f = v.f; c.c = v.c; c.color = v.color;
+        return c;
+    }
+    HVal prim(const Primary &p) {
+        if (p.is_const) return from_const(p.c);
+        if (p.value->index < 0) { HVal z; z.type = p.value->cv->type == T_FLOAT ? T_FLOAT : T_INT; return z; }
+        auto it = env.find(p.value);
+        if (it == env.end()) fail("internal error: frame-constant value used before definition");
+        return it->second;
+    }
+    static float as_float(const HVal &v) { return v.type == T_INT ? (float)v.i : v.f; }
+    static int as_int(const HVal &v) { return v.type == T_INT ? v.i : (int)v.f; }
+    static bool truth(const HVal &v) { return v.type == T_INT ? v.i != 0 : v.f != 0.0f; }
+    // C assignment into a variable of the compvar's type
+    static HVal coerce(HVal v, Type t) {
+        if (t == T_FLOAT && v.type == T_INT) { v.type = T_FLOAT; v.f = (float)v.i; }
+        else if (t == T_COMPLEX && v.type == T_INT) { v.type = T_COMPLEX; v.c = {(float)v.i, 0.f}; }
+        else if (t == T_COMPLEX && v.type == T_FLOAT) { v.type = T_COMPLEX; v.c = {v.f, 0.f}; }
+        return v;
+    }
+
+    int add_image(const HostImage &img) {
+        inv->images.push_back(img);
+        return (int)inv->images.size() - 1;
+    }
+
+    // render_image (builtins/builtins.c:269-345)
+    int render_image(int idx, int width, int height);
+    int gaussian_blur(const std::vector<HVal> &args);
+
+    HVal eval(const Rhs *r, const CompVar *dest) {
+        switch (r->kind) {
+        case RHS_PRIMARY: return prim(r->prim);
+        case RHS_INTERNAL: {
+            HVal v;
+            const std::string &n = r->internal;
+            if (n == "t") { v.type = T_FLOAT; v.f = t; }
+            else if (n == "R") { v.type = T_FLOAT; v.f = (float)sqrt(2.0); }
+            else if (n == "frame") { v.type = T_INT; v.i = frame; }
+            else if (n == "__canvasPixelW") { v.type = T_INT; v.i = inv->W; }
+            else if (n == "__canvasPixelH") { v.type = T_INT; v.i = inv->H; }
+            else if (n == "__renderPixelW") { v.type = T_INT; v.i = inv->W; }
+            else if (n == "__renderPixelH") { v.type = T_INT; v.i = inv->H; }
+            else fail("internal " + n + " is not frame-constant");
+            return v;
+        }
+        case RHS_TUPLE: {
+            HVal v;
+            v.type = T_TUPLE;
+            for (auto &a : r->args) v.tuple.push_back(as_float(prim(a)));
+            return v;
+        }
+        case RHS_CLOSURE: {
+            std::vector<HVal> args;
+            for (auto &a : r->args) args.push_back(prim(a));
+            HVal v;
+            v.type = T_IMAGE;
+            if (r->filter->kind == FILTER_NATIVE) {
+                if (r->filter->name == "gaussian_blur") v.image = gaussian_blur(args);
+                else fail("native filter " + r->filter->name + " is not implemented by the CUDA backend yet");
+                return v;
+            }
+            HostImage img;
+            img.kind = IMG_CLOSURE;
+            img.filter = r->filter;
+            // callee uservals are typed by the callee's declaration
+            for (size_t k = 0; k < args.size(); ++k)
+                if (r->filter->uservals[k].type == UV_FLOAT) args[k] = coerce(args[k], T_FLOAT);
+            img.args = args;
+            img.w = inv->W;
+            img.h = inv->H;
+            v.image = add_image(img);
+            return v;
+        }
+        case RHS_OP: break;
+        default: fail("internal error: rhs kind not frame-constant");
+        }
+        const OpInfo *op = r->op;
+        std::vector<HVal> a;
+        for (auto &p : r->args) a.push_back(prim(p));
+        HVal v;
+        switch (op->id) {
+        case OP_USERVAL_INT: case OP_USERVAL_BOOL: case OP_USERVAL_FLOAT: case OP_USERVAL_COLOR:
+        case OP_USERVAL_CURVE: case OP_USERVAL_GRADIENT: case OP_USERVAL_IMAGE: {
+            int idx = a[0].i;
+            if (idx < 0 || idx >= (int)uservals.size()) fail("userval index out of range");
+            return uservals[idx];
+        }
+        case OP_IMAGE_PIXEL_WIDTH: v.type = T_INT; v.i = inv->images.at(a[0].image).w; return v;
+        case OP_IMAGE_PIXEL_HEIGHT: v.type = T_INT; v.i = inv->images.at(a[0].image).h; return v;
+        case OP_RESIZE_IMAGE: {
+            HostImage img = inv->images.at(a[0].image);
+            if (img.kind == IMG_CLOSURE) fail("resizing a closure image that is not consumed by a direct call is not supported");
+            img.owned = false;
+            img.resized = true;
+            img.original = a[0].image;
+            img.xf = as_float(a[1]);
+            img.yf = as_float(a[2]);
+            v.type = T_IMAGE;
+            v.image = add_image(img);
+            return v;
+        }
+        case OP_STRIP_RESIZE: {
+            const HostImage &img = inv->images.at(a[0].image);
+            v.type = T_IMAGE;
+            v.image = img.resized ? img.original : a[0].image;
+            return v;
+        }
+        case OP_RENDER:
+            v.type = T_IMAGE;
+            v.image = render_image(a[0].image, as_int(a[1]), as_int(a[2]));
+            return v;
+        case OP_MAKE_RGBA_COLOR: {
+            auto q = [](float x) {
+                float cl = (0 < ((1 < x) ? 1 : x)) ? ((1 < x) ? 1 : x) : 0;
+                return (uint32_t)(int)(cl * 255) & 0xffu;
+            };
+            v.type = T_COLOR;
+            v.color = (q(as_float(a[0])) << 24) | (q(as_float(a[1])) << 16) | (q(as_float(a[2])) << 8) | q(as_float(a[3]));
+            return v;
+        }
+        case OP_RED: v.type = T_FLOAT; v.f = (float)((a[0].color >> 24) / 255.0); return v;
+        case OP_GREEN: v.type = T_FLOAT; v.f = (float)(((a[0].color >> 16) & 0xff) / 255.0); return v;
+        case OP_BLUE: v.type = T_FLOAT; v.f = (float)(((a[0].color >> 8) & 0xff) / 255.0); return v;
+        case OP_ALPHA: v.type = T_FLOAT; v.f = (float)((a[0].color & 0xff) / 255.0); return v;
+        case OP_TUPLE_NTH: {
+            int n = a[1].i;
+            v.type = T_FLOAT;
+            v.f = (n >= 0 && n < (int)a[0].tuple.size()) ? a[0].tuple[n] : 0.f;
+            return v;
+        }
+        default: break;
+        }
+        Const args[6], out;
+        for (int k = 0; k < op->nargs; ++k) args[k] = to_const(a[k]);
+        if (!eval_op(op, args, &out)) fail(std::string("op ") + op->name + " cannot be evaluated on the host");
+        (void)dest;
+        return from_const(out);
+    }
+
+    void set(const Value *lhs, HVal v) { env[lhs] = coerce(std::move(v), lhs->cv->type); }
+
+    void phis(const Stmt *p, int branch) {
+        std::vector<std::pair<const Value *, HVal>> vals;
+        for (; p; p = p->next)
+            if (p->kind == ST_PHI && p->lhs->level == 0) vals.push_back({p->lhs, eval(branch == 0 ? p->rhs : p->rhs2, p->lhs->cv)});
+        for (auto &kv : vals) set(kv.first, kv.second);
+    }
+    static bool has_level0(const Stmt *s) {
+        for (; s; s = s->next) {
+            switch (s->kind) {
+            case ST_ASSIGN: case ST_PHI: if (s->lhs->level == 0) return true; break;
+            case ST_IF: if (has_level0(s->cons) || has_level0(s->alt) || has_level0(s->exit)) return true; break;
+            case ST_WHILE: if (s->level == 0 || has_level0(s->body)) return true; break;
+            default: break;
+            }
+        }
+        return false;
+    }
+    void run(const Stmt *s) {
+        for (; s; s = s->next) {
+            switch (s->kind) {
+            case ST_ASSIGN:
+                if (s->lhs->level == 0) set(s->lhs, eval(s->rhs, s->lhs->cv));
+                break;
+            case ST_IF:
+                if (!(has_level0(s->cons) || has_level0(s->alt) || has_level0(s->exit))) break;
+                if (s->level == 0) {
+                    bool c = truth(eval(s->cond, nullptr));
+                    run(c ? s->cons : s->alt);
+                    phis(s->exit, c ? 0 : 1);
+                } else {  // condition is per-pixel: only speculated pure definitions live here
+                    run(s->cons);
+                    run(s->alt);
+                }
+                break;
+            case ST_WHILE:
+                if (s->level == 0) {
+                    phis(s->entry, 0);
+                    long guard = 0;
+                    while (truth(eval(s->cond, nullptr))) {
+                        run(s->body);
+                        phis(s->entry, 1);
+                        if (++guard > 100000000L) fail("frame-constant loop does not terminate");
+                    }
+                } else
+                    run(s->body);
+                break;
+            default: break;
+            }
+        }
+    }
+};
+
+// Packs the uniforms a filter's kernel reads and assigns image slots.
+void pack_frame(mmb_invocation *inv, const FilterKernel &k, Replay &rp, FrameData &fd) {
+    fd.uniforms.assign(k.uniforms_size, 0);
+    fd.nslots = 0;
+    std::map<int, int> slot_of;
+    for (const UniformField &u : k.uniforms) {
+        auto it = rp.env.find(u.value);
+        if (it == rp.env.end()) fail("internal error: uniform value was not computed by the host replay");
+        const HVal &v = it->second;
+        unsigned char *dst = fd.uniforms.data() + u.offset;
+        switch (u.type) {
+        case T_INT: case T_NIL: { int x = Replay::as_int(v); memcpy(dst, &x, 4); break; }
+        case T_FLOAT: { float x = Replay::as_float(v); memcpy(dst, &x, 4); break; }
+        case T_COMPLEX: { float z[2] = {v.c.real(), v.c.imag()}; memcpy(dst, z, 8); break; }
+        case T_COLOR: memcpy(dst, &v.color, 4); break;
+        case T_CURVE: case T_GRADIENT: memcpy(dst, &v.ptr, 8); break;
+        case T_IMAGE: {
+            int slot;
+            auto s = slot_of.find(v.image);
+            if (s != slot_of.end()) slot = s->second;
+            else {
+                if (v.image < 0 || v.image >= (int)inv->images.size()) fail("internal error: bad image handle");
+                const HostImage &img = inv->images[v.image];
+                if (img.kind == IMG_CLOSURE) fail("a closure image reaches per-pixel code without being called directly; this is not supported");
+                if (fd.nslots >= MM_MAX_IMAGES) fail("too many distinct images in one filter (max 16)");
+                slot = fd.nslots++;
+                fd.slots[slot] = to_device_desc(img);
+                slot_of[v.image] = slot;
+            }
+            memcpy(dst, &slot, 4);
+            break;
+        }
+        case T_TUPLE: {
+            for (int i = 0; i < std::max(1, u.tuple_len); ++i) {
+                float x = i < (int)v.tuple.size() ? v.tuple[i] : 0.f;
+                memcpy(dst + 4 * i, &x, 4);
+            }
+            break;
+        }
+        default: fail("internal error: unsupported uniform type");
+        }
+    }
+}
+
+struct LaunchGeom {
+    int frame_w, frame_h;   // frame_render_width/height the coordinates refer to
+    int region_x, region_w;
+    int first_row, num_rows;
+    float off_x, off_y;
+    int xs_count, ys_count;
+};
+
+void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, const LaunchGeom &g, void *out, long long out_stride, int floatmap,
+                   int frame, float t) {
+    std::string err;
+    auto lm = inv->backend->get(inv->cfg, inv->device, err);
+    if (!lm) fail(err);
+    DriverApi *api = driver_api(err);
+    if (!api) fail(err);
+    const FilterKernel &k = inv->backend->source.kernels.at(f);
+    mm_params P;
+    memset(&P, 0, sizeof P);
+    P.out = out;
+    P.out_stride = out_stride;
+    P.xs = coords(inv, false, g.frame_w, g.off_x, g.xs_count);
+    P.ys = coords(inv, true, g.frame_h, g.off_y, g.ys_count);
+    P.region_x = g.region_x;
+    P.region_y = 0;
+    P.region_w = g.region_w;
+    P.first_row = g.first_row;
+    P.num_rows = g.num_rows;
+    P.img_w = inv->W; P.img_h = inv->H; P.render_w = inv->W; P.render_h = inv->H;
+    P.frame = frame;
+    P.t = t;
+    P.R = (float)sqrt(2.0);
+    P.bpp = inv->bpp;
+    P.floatmap = floatmap;
+    P.edge_color_x = inv->edge_color_x;
+    P.edge_color_y = inv->edge_color_y;
+    for (int i = 0; i < fd.nslots; ++i) P.images[i] = fd.slots[i];
+    void *params[2] = {&P, (void *)fd.uniforms.data()};
+    unsigned gx = (unsigned)((g.region_w + 31) / 32), gy = (unsigned)((g.num_rows + 7) / 8);
+    if (gx == 0 || gy == 0) return;
+    int rc = api->launch_kernel(lm->functions.at(f), gx, gy, 1, 256, 1, 1, 0, inv->stream, params, nullptr);
+    if (rc != 0) fail("cuLaunchKernel(" + k.kernel_name + ") failed: " + api->error_string(rc));
+    inv->launches++;
+    inv->kernel_name = k.kernel_name;
+}
+
+int Replay::render_image(int idx, int width, int height) {
+    HostImage src = inv->images.at(idx);
+    if (src.kind == IMG_FLOATMAP) return idx;
+    HostImage out;
+    out.kind = IMG_FLOATMAP;
+    out.w = width;
+    out.h = height;
+    // floatmap_alloc, floatmap.c:30-47
+    out.ax = out.bx = (float)((float)(width - 1) / 2.0);
+    out.ay = out.by = (float)((float)(height - 1) / 2.0);
+    out.ay = (float)(out.ay * -1.0);
+    out.data = inv->alloc(sizeof(float) * 4 * (size_t)width * height);
+    if (src.kind == IMG_CLOSURE) {
+        if (depth > 16) fail("render() nesting too deep");
+        // a new frame for the closure: frame 0, t = 0.0 (builtins.c:288)
+        Replay sub(inv, src.filter, src.args, 0, 0.0f, depth + 1);
+        sub.run(sub.code->first);
+        const FilterKernel &k = inv->backend->source.kernels.at(src.filter);
+        FrameData fd;
+        pack_frame(inv, k, sub, fd);
+        LaunchGeom g{width, height, 0, width, 0, height, 0.f, 0.f, width, height};
+        launch_filter(inv, src.filter, fd, g, out.data, (long long)sizeof(float) * 4 * width, 1, 0, 0.0f);
+    } else {
+        mm_image d = to_device_desc(src);
+        launch_drawable_to_floatmap(d, (float *)out.data, width, height, out.ax, out.bx, out.ay, out.by, inv->cfg.edge_x, inv->cfg.edge_y,
+                                    inv->edge_color_x, inv->edge_color_y, inv->cfg.supersampling, inv->stream);
+        inv->launches++;
+    }
+    return add_image(out);
+}
+
+// native_filter_gaussian_blur, native-filters/gauss.c:643-670
+int Replay::gaussian_blur(const std::vector<HVal> &args) {
+    int in = args[0].image;
+    float h = as_float(args[1]), v = as_float(args[2]);
+    char key[128];
+    snprintf(key, sizeof key, "gauss:%d:%a:%a", in, (double)h, (double)v);
+    auto it = inv->native_cache.find(key);
+    if (it != inv->native_cache.end()) return it->second;
+    int fm = in;
+    if (inv->images.at(in).kind != IMG_FLOATMAP) fm = render_image(in, inv->W, inv->H);
+    HostImage src = inv->images.at(fm);
+    float sh = (float)fabs((double)(h * src.ax)), sv = (float)fabs((double)(v * src.ay));
+    HostImage out = src;
+    out.owned = false;
+    size_t bytes = sizeof(float) * 4 * (size_t)src.w * src.h;
+    out.data = inv->alloc(bytes);
+    if (sh < 0.5f || sv < 0.5f) {
+        void *tmp = inv->alloc(bytes);
+        if (!launch_gauss_rle((const float *)src.data, (float *)tmp, (float *)out.data, src.w, src.h, sh, sv, inv->stream))
+            fail("gaussian blur: unsupported kernel length");
+        inv->launches += 2;
+    } else {
+        ck(cudaMemcpyAsync(out.data, src.data, bytes, cudaMemcpyDeviceToDevice, inv->stream), "cudaMemcpyAsync(floatmap copy)");
+        void *scratch = inv->alloc(gauss_iir_scratch_bytes(src.w, src.h));
+        launch_gauss_iir((float *)out.data, (double *)scratch, src.w, src.h, sh, sv, inv->stream);
+        inv->launches += 2;
+    }
+    ck(cudaGetLastError(), "gaussian blur launch");
+    int idx = add_image(out);
+    inv->native_cache[key] = idx;
+    return idx;
+}
+
+std::vector<HVal> main_uservals(mmb_invocation *inv) {
+    std::vector<HVal> out;
+    for (auto &u : inv->uservals) {
+        HVal v;
+        switch (u.type) {
+        case UV_INT: case UV_BOOL: v.type = T_INT; v.i = u.i; break;
+        case UV_FLOAT: v.type = T_FLOAT; v.f = u.f; break;
+        case UV_COLOR: v.type = T_COLOR; v.color = u.color; break;
+        case UV_CURVE: v.type = T_CURVE; v.ptr = u.table ? u.table : inv->default_curve; break;
+        case UV_GRADIENT: v.type = T_GRADIENT; v.ptr = u.table ? u.table : inv->default_gradient; break;
+        case UV_IMAGE: v.type = T_IMAGE; v.image = u.image; break;
+        }
+        out.push_back(v);
+    }
+    return out;
+}
+
+void set_device(mmb_invocation *inv) { ck(cudaSetDevice(inv->device), "cudaSetDevice"); }
+
+template <class F> int guarded(F f) {
+    try {
+        f();
+        return 0;
+    } catch (Fail &e) {
+        set_error(e.msg);
+    } catch (mm::CompileError &e) {
+        set_error(e.message);
+    } catch (std::exception &e) {
+        set_error(std::string("internal error: ") + e.what());
+    }
+    return -1;
+}
+
+void render_band(mmb_invocation *inv, int first_row, int last_row, void *dev_out, int floatmap) {
+    if (!inv->frame_ready) fail("mmb_init_frame must be called before mmb_calc_lines");
+    first_row = std::max(0, first_row);
+    last_row = std::min(last_row, inv->H);
+    if (last_row <= first_row) return;
+    const Filter *f = inv->m->main;
+    int rows = last_row - first_row;
+    if (inv->cfg.supersampling && !floatmap) {
+        // call_invocation, mathmap_common.c:880-927: the short slice plus a one-column-wider
+        // slice sampled at (-0.5, -0.5), combined (l1[c] + l1[c+1] + 2 l2[c] + l3[c] + l3[c+1]) / 6
+        int bpp = inv->bpp;
+        int long_rows = std::min(last_row + 1, inv->H) - first_row;
+        void *s = inv->ensure_staging(inv->staging2, inv->staging2_bytes, (size_t)rows * inv->W * bpp + (size_t)(rows + 1) * (inv->W + 1) * bpp + 512);
+        unsigned char *shortimg = (unsigned char *)s;
+        unsigned char *longimg = shortimg + (((size_t)rows * inv->W * bpp + 255) & ~(size_t)255);
+        LaunchGeom gs{inv->W, inv->H, 0, inv->W, first_row, rows, 0.f, 0.f, inv->W + 1, inv->H + 1};
+        launch_filter(inv, f, inv->main_frame, gs, shortimg, (long long)inv->W * bpp, 0, inv->frame, inv->t);
+        LaunchGeom gl{inv->W, inv->H, 0, inv->W + 1, first_row, long_rows, -0.5f, -0.5f, inv->W + 1, inv->H + 1};
+        launch_filter(inv, f, inv->main_frame, gl, longimg, (long long)(inv->W + 1) * bpp, 0, inv->frame, inv->t);
+        // rows of the long image beyond what was rendered repeat the last one
+        launch_supersample_combine(shortimg, longimg, (unsigned char *)dev_out, inv->W, rows, long_rows, bpp, inv->stream);
+        inv->launches++;
+        ck(cudaGetLastError(), "supersample combine");
+        return;
+    }
+    LaunchGeom g{inv->W, inv->H, 0, inv->W, first_row, rows, 0.f, 0.f, inv->W + 1, inv->H + 1};
+    long long stride = floatmap ? (long long)sizeof(float) * 4 * inv->W : (long long)inv->W * inv->bpp;
+    launch_filter(inv, f, inv->main_frame, g, dev_out, stride, floatmap, inv->frame, inv->t);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char *mmb_module_cuda_source(mmb_module *m) {
+    if (!m) return nullptr;
+    int rc = guarded([&] { get_module_backend(m); });
+    return rc == 0 ? m->cuda_source.c_str() : nullptr;
+}
+
+// Build check without a GPU: NVRTC-compiles the module for sm_100a; returns cubin bytes or -1.
+long mmb_module_compile_check(mmb_module *m, int antialiasing, int precise_math) {
+    if (!m) return -1;
+    KernelConfig cfg;
+    cfg.aa = antialiasing;
+    cfg.precise = precise_math;
+    std::string err;
+    long n = compile_only(m, cfg, err);
+    if (n < 0) set_error(err);
+    return n;
+}
+
+mmb_invocation *mmb_invoke(mmb_module *m, int img_width, int img_height, int device) {
+    if (!m || img_width <= 0 || img_height <= 0) { set_error("mmb_invoke: bad arguments"); return nullptr; }
+    auto inv = new mmb_invocation();
+    int rc = guarded([&] {
+        inv->m = m;
+        inv->device = device;
+        inv->W = img_width;
+        inv->H = img_height;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            fail(std::string("no CUDA device available (") + cudaGetErrorString(e) + "); mathmap_b200 has no CPU path");
+        if (device < 0 || device >= count) fail("CUDA device ordinal out of range");
+        set_device(inv);
+        ck(cudaFree(nullptr), "CUDA context creation");
+        inv->backend = get_module_backend(m);
+        for (auto &u : m->main->uservals) {
+            Userval v;
+            v.type = u.type;
+            switch (u.type) {
+            case UV_INT: v.i = u.int_default; break;
+            case UV_FLOAT: v.f = u.float_default; break;
+            case UV_BOOL: v.i = u.bool_default; break;
+            case UV_COLOR: v.color = 0x000000ffu; break;  // opaque black
+            default: break;
+            }
+            inv->uservals.push_back(v);
+        }
+        // default curve: identity; default gradient: gray ramp (userval.c:281-309, mathmap.c:356-361)
+        std::vector<float> curve(MMB_CURVE_POINTS);
+        std::vector<uint32_t> grad(MMB_CURVE_POINTS);
+        for (int i = 0; i < MMB_CURVE_POINTS; ++i) {
+            curve[i] = (float)i / (float)(MMB_CURVE_POINTS - 1);
+            uint32_t g = (uint32_t)(int)((double)i / (MMB_CURVE_POINTS - 1) * 255.0);
+            grad[i] = (g << 24) | (g << 16) | (g << 8) | 255u;
+        }
+        ck(cudaMalloc(&inv->default_curve, sizeof(float) * MMB_CURVE_POINTS), "cudaMalloc");
+        ck(cudaMalloc(&inv->default_gradient, sizeof(uint32_t) * MMB_CURVE_POINTS), "cudaMalloc");
+        ck(cudaMemcpy(inv->default_curve, curve.data(), sizeof(float) * MMB_CURVE_POINTS, cudaMemcpyHostToDevice), "cudaMemcpy");
+        ck(cudaMemcpy(inv->default_gradient, grad.data(), sizeof(uint32_t) * MMB_CURVE_POINTS, cudaMemcpyHostToDevice), "cudaMemcpy");
+    });
+    if (rc != 0) { delete inv; return nullptr; }
+    return inv;
+}
+
+void mmb_invocation_free(mmb_invocation *inv) {
+    if (!inv) return;
+    cudaSetDevice(inv->device);
+    cudaStreamSynchronize(inv->stream);
+    inv->release_frame_blocks();
+    for (auto &b : inv->free_blocks) cudaFree(b.second);
+    for (auto &img : inv->images)
+        if (img.owned && img.data) cudaFree(img.data);
+    for (auto &u : inv->uservals)
+        if (u.table) cudaFree(u.table);
+    for (auto &c : inv->coord_cache) cudaFree(c.second);
+    if (inv->staging) cudaFree(inv->staging);
+    if (inv->staging2) cudaFree(inv->staging2);
+    if (inv->default_curve) cudaFree(inv->default_curve);
+    if (inv->default_gradient) cudaFree(inv->default_gradient);
+    delete inv;
+}
+
+int mmb_set_antialiasing(mmb_invocation *inv, int enabled) { inv->cfg.aa = enabled ? 1 : 0; return 0; }
+int mmb_set_supersampling(mmb_invocation *inv, int enabled) { inv->cfg.supersampling = enabled ? 1 : 0; return 0; }
+int mmb_set_precise_math(mmb_invocation *inv, int enabled) { inv->cfg.precise = enabled ? 1 : 0; return 0; }
+int mmb_set_warp_shape(mmb_invocation *inv, int warp_width) {
+    if (warp_width != 32 && warp_width != 16 && warp_width != 8) { set_error("warp width must be 32, 16 or 8"); return -1; }
+    inv->cfg.warp_w = warp_width;
+    return 0;
+}
+int mmb_set_edge_behaviour(mmb_invocation *inv, int mode_x, int mode_y, uint32_t color_x, uint32_t color_y) {
+    if (mode_x < 0 || mode_x > 3 || mode_y < 0 || mode_y > 3) { set_error("bad edge behaviour"); return -1; }
+    inv->cfg.edge_x = mode_x;
+    inv->cfg.edge_y = mode_y;
+    inv->edge_color_x = color_x;
+    inv->edge_color_y = color_y;
+    return 0;
+}
+int mmb_set_output_bpp(mmb_invocation *inv, int bpp) {
+    if (bpp < 1 || bpp > 4) { set_error("output bpp must be 1..4"); return -1; }
+    inv->bpp = bpp;
+    return 0;
+}
+
+static Userval *userval_slot(mmb_invocation *inv, int index, int type) {
+    if (!inv || index < 0 || index >= (int)inv->uservals.size()) { set_error("userval index out of range"); return nullptr; }
+    if (inv->uservals[index].type != type) {
+        set_error(std::string("userval ") + inv->m->main->uservals[index].name + " is of type " + userval_type_name(inv->uservals[index].type));
+        return nullptr;
+    }
+    inv->frame_ready = false;
+    return &inv->uservals[index];
+}
+int mmb_set_userval_int(mmb_invocation *inv, int index, int value) {
+    Userval *u = userval_slot(inv, index, UV_INT);
+    if (!u) return -1;
+    u->i = value;
+    return 0;
+}
+int mmb_set_userval_float(mmb_invocation *inv, int index, float value) {
+    Userval *u = userval_slot(inv, index, UV_FLOAT);
+    if (!u) return -1;
+    u->f = value;
+    return 0;
+}
+int mmb_set_userval_bool(mmb_invocation *inv, int index, int value) {
+    Userval *u = userval_slot(inv, index, UV_BOOL);
+    if (!u) return -1;
+    u->i = value ? 1 : 0;
+    return 0;
+}
+int mmb_set_userval_color(mmb_invocation *inv, int index, float r, float g, float b, float a) {
+    Userval *u = userval_slot(inv, index, UV_COLOR);
+    if (!u) return -1;
+    auto q = [](float x) { x = x < 0 ? 0 : (x > 1 ? 1 : x); return (uint32_t)(int)(x * 255.0) & 0xffu; };  // MAKE_RGBA_COLOR_FLOAT, color.h:40
+    u->color = (q(r) << 24) | (q(g) << 16) | (q(b) << 8) | q(a);
+    return 0;
+}
+static int set_table(mmb_invocation *inv, int index, int type, const void *host, size_t bytes) {
+    Userval *u = userval_slot(inv, index, type);
+    if (!u) return -1;
+    return guarded([&] {
+        set_device(inv);
+        if (!u->table) ck(cudaMalloc(&u->table, bytes), "cudaMalloc");
+        ck(cudaMemcpy(u->table, host, bytes, cudaMemcpyHostToDevice), "cudaMemcpy");
+    });
+}
+int mmb_set_userval_curve(mmb_invocation *inv, int index, const float *values) {
+    return set_table(inv, index, UV_CURVE, values, sizeof(float) * MMB_CURVE_POINTS);
+}
+int mmb_set_userval_gradient(mmb_invocation *inv, int index, const uint32_t *rgba_packed) {
+    return set_table(inv, index, UV_GRADIENT, rgba_packed, sizeof(uint32_t) * MMB_CURVE_POINTS);
+}
+
+static int set_image(mmb_invocation *inv, int index, const void *data, bool host, int width, int height) {
+    Userval *u = userval_slot(inv, index, UV_IMAGE);
+    if (!u) return -1;
+    if (width <= 0 || height <= 0 || !data) { set_error("bad image"); return -1; }
+    return guarded([&] {
+        set_device(inv);
+        if (inv->images.size() != inv->persistent_images) {  // drop per-frame images before touching the persistent prefix
+            inv->images.resize(inv->persistent_images);
+            inv->native_cache.clear();
+        }
+        HostImage img;
+        img.kind = IMG_DRAWABLE;
+        img.w = width;
+        img.h = height;
+        // calc_image_values, userval.c:263-279
+        img.sx = (float)((width - 1) / 2.0);
+        img.sy = (float)((height - 1) / 2.0);
+        img.mx = 1.0f;
+        img.my = 1.0f;
+        size_t bytes = (size_t)width * height * 4;
+        int slot = u->image;
+        if (host) {
+            void *d = nullptr;
+            if (slot >= 0 && inv->images[slot].owned && (size_t)inv->images[slot].w * inv->images[slot].h * 4 == bytes) d = inv->images[slot].data;
+            else {
+                if (slot >= 0 && inv->images[slot].owned) cudaFree(inv->images[slot].data);
+                ck(cudaMalloc(&d, bytes), "cudaMalloc(image)");
+            }
+            ck(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, inv->stream), "cudaMemcpyAsync(image)");
+            img.data = d;
+            img.owned = true;
+        } else {
+            if (slot >= 0 && inv->images[slot].owned) cudaFree(inv->images[slot].data);
+            img.data = const_cast<void *>(data);
+            img.owned = false;
+        }
+        if (slot >= 0) inv->images[slot] = img;
+        else {
+            inv->images.push_back(img);
+            u->image = (int)inv->images.size() - 1;
+            inv->persistent_images = inv->images.size();
+        }
+    });
+}
+int mmb_set_userval_image_host(mmb_invocation *inv, int index, const uint8_t *rgba, int width, int height) {
+    return set_image(inv, index, rgba, true, width, height);
+}
+int mmb_set_userval_image_device(mmb_invocation *inv, int index, const void *device_rgba, int width, int height) {
+    return set_image(inv, index, device_rgba, false, width, height);
+}
+
+int mmb_init_frame(mmb_invocation *inv, int frame, float t) {
+    if (!inv) return -1;
+    return guarded([&] {
+        set_device(inv);
+        for (size_t i = 0; i < inv->uservals.size(); ++i)
+            if (inv->uservals[i].type == UV_IMAGE && inv->uservals[i].image < 0) {
+                // the reference samples white from a missing drawable (builtins.c:125-126); we require the binding
+                fail("image argument `" + inv->m->main->uservals[i].name + "' has no drawable bound");
+            }
+        // previous frame's temporaries become reusable (same stream: ordering is preserved)
+        inv->release_frame_blocks();
+        inv->images.resize(inv->persistent_images);
+        inv->native_cache.clear();
+        inv->frame = frame;
+        inv->t = t;
+        std::vector<HVal> uv = main_uservals(inv);
+        Replay rp(inv, inv->m->main, uv, frame, t, 0);
+        rp.run(rp.code->first);
+        pack_frame(inv, inv->backend->source.kernels.at(inv->m->main), rp, inv->main_frame);
+        inv->frame_ready = true;
+    });
+}
+
+int mmb_calc_lines_device(mmb_invocation *inv, int first_row, int last_row, void *device_q, int floatmap, void *stream) {
+    if (!inv || !device_q) { set_error("mmb_calc_lines_device: bad arguments"); return -1; }
+    return guarded([&] {
+        set_device(inv);
+        cudaStream_t saved = inv->stream;
+        if (stream) inv->stream = (cudaStream_t)stream;
+        try {
+            render_band(inv, first_row, last_row, device_q, floatmap);
+        } catch (...) {
+            inv->stream = saved;
+            throw;
+        }
+        inv->stream = saved;
+    });
+}
+
+int mmb_calc_lines(mmb_invocation *inv, int first_row, int last_row, void *q, int floatmap) {
+    if (!inv || !q) { set_error("mmb_calc_lines: bad arguments"); return -1; }
+    return guarded([&] {
+        set_device(inv);
+        int fr = std::max(0, first_row), lr = std::min(last_row, inv->H);
+        if (lr <= fr) return;
+        size_t row_bytes = floatmap ? sizeof(float) * 4 * (size_t)inv->W : (size_t)inv->W * inv->bpp;
+        size_t bytes = row_bytes * (size_t)(lr - fr);
+        void *d = inv->ensure_staging(inv->staging, inv->staging_bytes, bytes);
+        render_band(inv, fr, lr, d, floatmap);
+        ck(cudaMemcpyAsync(q, d, bytes, cudaMemcpyDeviceToHost, inv->stream), "cudaMemcpyAsync(D2H)");
+        ck(cudaStreamSynchronize(inv->stream), "cudaStreamSynchronize");
+    });
+}
+
+int mmb_render_frames_device(mmb_invocation *inv, int n, const int *frames, const float *ts, void *device_q, void *stream) {
+    if (!inv || !device_q || n < 0) { set_error("mmb_render_frames_device: bad arguments"); return -1; }
+    size_t frame_bytes = (size_t)inv->W * inv->H * inv->bpp;
+    for (int i = 0; i < n; ++i) {
+        if (mmb_init_frame(inv, frames ? frames[i] : i, ts[i]) != 0) return -1;
+        if (mmb_calc_lines_device(inv, 0, inv->H, (char *)device_q + frame_bytes * i, 0, stream) != 0) return -1;
+    }
+    return 0;
+}
+
+int mmb_synchronize(mmb_invocation *inv) {
+    return guarded([&] {
+        set_device(inv);
+        ck(cudaStreamSynchronize(inv->stream), "cudaStreamSynchronize");
+        ck(cudaGetLastError(), "kernel execution");
+    });
+}
+
+long mmb_launch_count(const mmb_invocation *inv) { return inv ? inv->launches : -1; }
+const char *mmb_kernel_name(const mmb_invocation *inv) { return inv ? inv->kernel_name.c_str() : nullptr; }
+
+int mmb_gaussian_blur_device(int device, const float *device_in, float *device_out, int width, int height, float sigma_h_px, float sigma_v_px,
+                             void *stream) {
+    return guarded([&] {
+        ck(cudaSetDevice(device), "cudaSetDevice");
+        cudaStream_t s = (cudaStream_t)stream;
+        size_t bytes = sizeof(float) * 4 * (size_t)width * height;
+        if (sigma_h_px < 0.5f || sigma_v_px < 0.5f) {
+            void *tmp = nullptr;
+            ck(cudaMalloc(&tmp, bytes), "cudaMalloc");
+            bool ok = launch_gauss_rle(device_in, (float *)tmp, device_out, width, height, sigma_h_px, sigma_v_px, s);
+            cudaStreamSynchronize(s);
+            cudaFree(tmp);
+            if (!ok) fail("gaussian blur: unsupported kernel length");
+        } else {
+            void *scratch = nullptr;
+            ck(cudaMalloc(&scratch, gauss_iir_scratch_bytes(width, height)), "cudaMalloc(scratch)");
+            if (device_out != device_in) ck(cudaMemcpyAsync(device_out, device_in, bytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync");
+            launch_gauss_iir(device_out, (double *)scratch, width, height, sigma_h_px, sigma_v_px, s);
+            cudaStreamSynchronize(s);
+            cudaFree(scratch);
+        }
+        ck(cudaGetLastError(), "gaussian blur");
+    });
+}
+
+// test hook: the IIR coefficients the host computes (30 doubles: n_p n_m d_p d_m bd_p bd_m)
+void mmb_gauss_iir_constants(float std_dev, double *out30) { gauss_iir_constants_host(std_dev, out30); }
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// NVRTC compilation (sm_100a) and module loading for generated filter kernels.
+// Takes the place of the reference's "write C, run gcc, g_module_open" step
+// (backends/cc.c:634-758).
+#pragma once
+#include <cuda_runtime_api.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "cuda_emit.h"
+
+namespace mmbackend {
+
+void set_error(const std::string &msg);
+
+struct KernelConfig {
+    int aa = 0, supersampling = 0, edge_x = 0, edge_y = 0, precise = 0, warp_w = 32;
+    std::string key() const;
+};
+
+// Minimal slice of the CUDA driver API, resolved through the runtime
+// (cudaGetDriverEntryPoint) so the library has no link-time dependency on libcuda.
+struct DriverApi {
+    typedef int (*ModuleLoadData)(void **module, const void *image);
+    typedef int (*ModuleGetFunction)(void **func, void *module, const char *name);
+    typedef int (*ModuleUnload)(void *module);
+    typedef int (*LaunchKernel)(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned smem, void *stream,
+                                void **params, void **extra);
+    typedef int (*GetErrorString)(int err, const char **str);
+    ModuleLoadData module_load_data = nullptr;
+    ModuleGetFunction module_get_function = nullptr;
+    ModuleUnload module_unload = nullptr;
+    LaunchKernel launch_kernel = nullptr;
+    GetErrorString get_error_string = nullptr;
+    bool load(std::string &err);
+    std::string error_string(int code) const;
+};
+DriverApi *driver_api(std::string &err);
+
+struct LoadedModule {
+    void *module = nullptr;
+    std::map<const mm::Filter *, void *> functions;
+    ~LoadedModule();
+};
+
+// Everything the backend keeps per mmb_module: the generated source, the cubins
+// per kernel configuration and the loaded modules per (configuration, device).
+struct ModuleBackend {
+    CudaModuleSource source;
+    std::mutex mu;
+    std::map<std::string, std::string> cubins;                         // config key -> cubin bytes
+    std::map<std::string, std::shared_ptr<LoadedModule>> loaded;       // config key + device -> module
+    std::string full_source(const KernelConfig &cfg) const;            // what NVRTC sees (for inspection)
+    std::shared_ptr<LoadedModule> get(const KernelConfig &cfg, int device, std::string &err);
+    double last_compile_ms = 0.0;
+};
+
+std::shared_ptr<ModuleBackend> get_module_backend(mmb_module *m);  // creates on first use; throws mm::CompileError
+
+}  // namespace mmbackend

@@ -1,0 +1,395 @@
+// mathmap_b200 device runtime (sm_100a).  Hand-written device functions the
+// NVRTC-generated filter kernels are compiled together with.  It replaces the
+// C runtime the reference's generated code links against:
+//   op semantics ................. reference opmacros.h:30-216, ops.lisp:112-253
+//   sampling, edge behaviour ..... reference builtins/builtins.c:41-265, color.h:36-54
+//   output quantisation .......... reference new_template.c.in:272-293
+// Numeric contract: every IR op result is rounded to float32 (the reference
+// stores each op in a float C variable); the translation unit is compiled with
+// --fmad=false so + - * are never contracted; libm calls follow MM_PRECISE
+// (1: evaluated in double and narrowed, like the host's double libm on float
+// arguments; 0: CUDA's float libm, <= 2 ulp).  Integer work (texel addressing,
+// rounding of bilinear sums to 8 bits, truncating output quantisation) is
+// bit-exact in both modes.
+//
+// Compile-time configuration (set by backend/nvrtc_module.cpp):
+//   MM_AA            1: bilinear sampler (cmdline -i), 0: nearest
+//   MM_SUPERSAMPLING 1: nearest sampler omits the +0.5 (builtins.c:155-159)
+//   MM_EDGE_X/Y      0 colour, 1 wrap, 2 reflect, 3 rotate
+//   MM_PRECISE       see above
+#pragma once
+
+#ifndef MM_AA
+#define MM_AA 0
+#endif
+#ifndef MM_SUPERSAMPLING
+#define MM_SUPERSAMPLING 0
+#endif
+#ifndef MM_EDGE_X
+#define MM_EDGE_X 0
+#endif
+#ifndef MM_EDGE_Y
+#define MM_EDGE_Y 0
+#endif
+#ifndef MM_PRECISE
+#define MM_PRECISE 0
+#endif
+
+#define MM_DEV __device__ __forceinline__
+
+// Pixel-grid launch geometry: 1-D blocks of 256 threads, each block renders a
+// 32 x 8 pixel tile; MM_WARP_W selects the footprint of one warp inside the tile
+// (32: one 128-byte output row segment per warp store; 8: an 8 x 4 patch, which
+// keeps divergent filters -- escape-time loops, data-dependent taps -- more
+// coherent and gathers more local).
+#ifndef MM_WARP_W
+#define MM_WARP_W 32
+#endif
+#define MM_BLOCK_W 32
+#define MM_BLOCK_H 8
+MM_DEV void mm_pixel_coords(int &col, int &row) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if MM_WARP_W == 32
+    col = blockIdx.x * MM_BLOCK_W + lane;
+    row = blockIdx.y * MM_BLOCK_H + warp;
+#elif MM_WARP_W == 16
+    col = blockIdx.x * MM_BLOCK_W + (warp & 1) * 16 + (lane & 15);
+    row = blockIdx.y * MM_BLOCK_H + (warp >> 1) * 2 + (lane >> 4);
+#else
+    col = blockIdx.x * MM_BLOCK_W + (warp & 3) * 8 + (lane & 7);
+    row = blockIdx.y * MM_BLOCK_H + (warp >> 2) * 4 + (lane >> 3);
+#endif
+}
+#include "mm_types.h"
+
+template <int N> struct mm_tup { float v[N]; };
+
+// ---------------------------------------------------------------- conversions
+// float/double -> int with x86 cvttss2si semantics (out of range and NaN give
+// INT_MIN), which is what the reference's C casts do on its host.
+MM_DEV int mm_f2i(float f) {
+    if (!(f > -2147483904.0f && f < 2147483648.0f)) return (int)0x80000000;
+    return __float2int_rz(f);
+}
+MM_DEV int mm_d2i(double d) {
+    if (!(d > -2147483649.0 && d < 2147483648.0)) return (int)0x80000000;
+    return __double2int_rz(d);
+}
+
+// ------------------------------------------------------------------- scalar ops
+// MIN/MAX are the template's macros: (a<b)?a:b and (a<b)?b:a (new_template.c.in:51-56)
+MM_DEV float mm_min(float a, float b) { return (a < b) ? a : b; }
+MM_DEV float mm_max(float a, float b) { return (a < b) ? b : a; }
+MM_DEV int mm_min(int a, int b) { return (a < b) ? a : b; }
+MM_DEV int mm_max(int a, int b) { return (a < b) ? b : a; }
+MM_DEV float mm_clamp01(float x) { return mm_max(0.0f, mm_min(1.0f, x)); }
+MM_DEV float mm_div(float a, float b) { return __fdiv_rn(a, b); }
+MM_DEV float mm_mod(float a, float b) { return fmodf(a, b); }  // fmod is exact: float result == double result
+MM_DEV float mm_sqrt(float a) { return __fsqrt_rn(a); }        // == (float)sqrt((double)a)
+MM_DEV float mm_hypot(float a, float b) {
+    // (float)hypot((double)a,(double)b): squares are exact in double
+    double s = __dadd_rn(__dmul_rn((double)a, (double)a), __dmul_rn((double)b, (double)b));
+    return (float)__dsqrt_rn(s);
+}
+MM_DEV int mm_floor(float a) { return mm_f2i(floorf(a)); }
+MM_DEV int mm_ceil(float a) { return mm_f2i(ceilf(a)); }
+MM_DEV float mm_abs(float a) { return fabsf(a); }
+MM_DEV int mm_abs(int a) { return mm_d2i(fabs((double)a)); }
+
+#if MM_PRECISE
+#define MM_LIBM1(name, fn) MM_DEV float name(float a) { return (float)fn((double)a); }
+#define MM_LIBM2(name, fn) MM_DEV float name(float a, float b) { return (float)fn((double)a, (double)b); }
+#else
+#define MM_LIBM1(name, fn) MM_DEV float name(float a) { return fn##f(a); }
+#define MM_LIBM2(name, fn) MM_DEV float name(float a, float b) { return fn##f(a, b); }
+#endif
+MM_LIBM1(mm_sin, sin)
+MM_LIBM1(mm_cos, cos)
+MM_LIBM1(mm_tan, tan)
+MM_LIBM1(mm_asin, asin)
+MM_LIBM1(mm_acos, acos)
+MM_LIBM1(mm_atan, atan)
+MM_LIBM2(mm_atan2, atan2)
+MM_LIBM2(mm_pow, pow)
+MM_LIBM1(mm_exp, exp)
+MM_LIBM1(mm_log, log)
+MM_LIBM1(mm_sinh, sinh)
+MM_LIBM1(mm_cosh, cosh)
+MM_LIBM1(mm_tanh, tanh)
+MM_LIBM1(mm_asinh, asinh)
+MM_LIBM1(mm_acosh, acosh)
+MM_LIBM1(mm_atanh, atanh)
+// GSL's gsl_sf_gamma / gsl_sf_beta are third-party and absent; tgamma/lgamma based (parity unpinned)
+MM_DEV float mm_gamma(float a) { return ((double)a > 171.0) ? 0.0f : (float)tgamma((double)a); }
+MM_DEV float mm_beta(float a, float b) { return (float)exp(lgamma((double)a) + lgamma((double)b) - lgamma((double)a + (double)b)); }
+
+// ---------------------------------------------------------------------- complex
+// float _Complex as float2.  Functions are evaluated in double and narrowed (the
+// host uses glibc's float complex functions, themselves accurate to < 1 ulp).
+struct mm_cd { double re, im; };
+MM_DEV mm_cd mm_cd_of(float2 z) { mm_cd r; r.re = z.x; r.im = z.y; return r; }
+MM_DEV float2 mm_c_narrow(mm_cd z) { return make_float2((float)z.re, (float)z.im); }
+MM_DEV mm_cd mm_cd_mul(mm_cd a, mm_cd b) { mm_cd r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
+MM_DEV mm_cd mm_cd_div(mm_cd a, mm_cd b) {
+    double d = b.re * b.re + b.im * b.im;
+    mm_cd r; r.re = (a.re * b.re + a.im * b.im) / d; r.im = (a.im * b.re - a.re * b.im) / d; return r;
+}
+MM_DEV mm_cd mm_cd_exp(mm_cd z) { double e = exp(z.re), s, c; sincos(z.im, &s, &c); mm_cd r; r.re = e * c; r.im = e * s; return r; }
+MM_DEV mm_cd mm_cd_log(mm_cd z) { mm_cd r; r.re = 0.5 * log(z.re * z.re + z.im * z.im); r.im = atan2(z.im, z.re); return r; }
+MM_DEV mm_cd mm_cd_sqrt(mm_cd z) {
+    mm_cd r;
+    if (z.re == 0.0 && z.im == 0.0) { r.re = 0.0; r.im = z.im; return r; }
+    double m = hypot(z.re, z.im);
+    if (z.re >= 0.0) { double t = sqrt(0.5 * (m + z.re)); r.re = t; r.im = z.im / (2.0 * t); }
+    else { double t = sqrt(0.5 * (m - z.re)); r.re = fabs(z.im) / (2.0 * t); r.im = copysign(t, z.im); }
+    return r;
+}
+MM_DEV mm_cd mm_cd_make(double re, double im) { mm_cd r; r.re = re; r.im = im; return r; }
+
+MM_DEV float2 mm_complex(float re, float im) { return make_float2(re, im); }
+MM_DEV float mm_creal(float2 z) { return z.x; }
+MM_DEV float mm_cimag(float2 z) { return z.y; }
+MM_DEV float2 mm_cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+MM_DEV float2 mm_csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+MM_DEV float2 mm_cneg(float2 a) { return make_float2(-a.x, -a.y); }
+MM_DEV float2 mm_cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+MM_DEV float2 mm_csqrt(float2 z) { return mm_c_narrow(mm_cd_sqrt(mm_cd_of(z))); }
+MM_DEV float2 mm_cexp(float2 z) {
+    // glibc cexpf: expf(re) * (cosf(im), sinf(im)), each factor rounded to float first
+    float e = mm_exp(z.x), s = mm_sin(z.y), c = mm_cos(z.y);
+    return make_float2(e * c, e * s);
+}
+MM_DEV float2 mm_clog(float2 z) { return mm_c_narrow(mm_cd_log(mm_cd_of(z))); }
+MM_DEV float mm_carg(float2 z) { return mm_atan2(z.y, z.x); }
+MM_DEV float2 mm_cpow(float2 a, float2 b) {
+    // glibc cpowf(x, c) = cexpf(c * clogf(x)) in float complex arithmetic
+    float2 l = mm_clog(a);
+    return mm_cexp(mm_cmul(b, l));
+}
+MM_DEV float2 mm_csin(float2 z) {
+    double s, c; sincos((double)z.x, &s, &c);
+    return make_float2((float)(s * cosh((double)z.y)), (float)(c * sinh((double)z.y)));
+}
+MM_DEV float2 mm_ccos(float2 z) {
+    double s, c; sincos((double)z.x, &s, &c);
+    return make_float2((float)(c * cosh((double)z.y)), (float)(-s * sinh((double)z.y)));
+}
+MM_DEV float2 mm_ctan(float2 z) {
+    double s, c; sincos(2.0 * (double)z.x, &s, &c);
+    double d = c + cosh(2.0 * (double)z.y);
+    return make_float2((float)(s / d), (float)(sinh(2.0 * (double)z.y) / d));
+}
+MM_DEV float2 mm_csinh(float2 z) {
+    double s, c; sincos((double)z.y, &s, &c);
+    return make_float2((float)(sinh((double)z.x) * c), (float)(cosh((double)z.x) * s));
+}
+MM_DEV float2 mm_ccosh(float2 z) {
+    double s, c; sincos((double)z.y, &s, &c);
+    return make_float2((float)(cosh((double)z.x) * c), (float)(sinh((double)z.x) * s));
+}
+MM_DEV float2 mm_ctanh(float2 z) {
+    double s, c; sincos(2.0 * (double)z.y, &s, &c);
+    double d = cosh(2.0 * (double)z.x) + c;
+    return make_float2((float)(sinh(2.0 * (double)z.x) / d), (float)(s / d));
+}
+MM_DEV mm_cd mm_cd_asinh(mm_cd z) {
+    mm_cd z2 = mm_cd_mul(z, z);
+    z2.re += 1.0;
+    mm_cd s = mm_cd_sqrt(z2);
+    return mm_cd_log(mm_cd_make(z.re + s.re, z.im + s.im));
+}
+MM_DEV float2 mm_casinh(float2 z) { return mm_c_narrow(mm_cd_asinh(mm_cd_of(z))); }
+MM_DEV float2 mm_casin(float2 z) {  // -i * asinh(i z)
+    mm_cd w = mm_cd_asinh(mm_cd_make(-(double)z.y, (double)z.x));
+    return mm_c_narrow(mm_cd_make(w.im, -w.re));
+}
+MM_DEV float2 mm_cacos(float2 z) {
+    mm_cd w = mm_cd_asinh(mm_cd_make(-(double)z.y, (double)z.x));
+    return mm_c_narrow(mm_cd_make(1.5707963267948966 - w.im, w.re));
+}
+MM_DEV float2 mm_cacosh(float2 z) {
+    mm_cd a = mm_cd_sqrt(mm_cd_make((double)z.x + 1.0, (double)z.y)), b = mm_cd_sqrt(mm_cd_make((double)z.x - 1.0, (double)z.y));
+    mm_cd p = mm_cd_mul(a, b);
+    return mm_c_narrow(mm_cd_log(mm_cd_make((double)z.x + p.re, (double)z.y + p.im)));
+}
+MM_DEV mm_cd mm_cd_atanh(mm_cd z) {
+    mm_cd a = mm_cd_log(mm_cd_make(1.0 + z.re, z.im)), b = mm_cd_log(mm_cd_make(1.0 - z.re, -z.im));
+    return mm_cd_make(0.5 * (a.re - b.re), 0.5 * (a.im - b.im));
+}
+MM_DEV float2 mm_catanh(float2 z) { return mm_c_narrow(mm_cd_atanh(mm_cd_of(z))); }
+MM_DEV float2 mm_catan(float2 z) {  // -i * atanh(i z)
+    mm_cd w = mm_cd_atanh(mm_cd_make(-(double)z.y, (double)z.x));
+    return mm_c_narrow(mm_cd_make(w.im, -w.re));
+}
+// complex gamma: Luke's 7-term approximation in complex double with reflection
+// for Re z < 0 (reference builtins/spec_func.c:35-63)
+__device__ __noinline__ float2 mm_cgamma(float2 zf) {
+    const double coeff[7] = {41.624436916439068, -51.224241022374774, 11.338755813488977, -0.747732687772388,
+                             0.008782877493061,  -1.899030264e-6,     1.946335e-9};
+    mm_cd z = mm_cd_of(zf), denom = mm_cd_make(1.0, 0.0);
+    if (z.re < 0.0) {
+        int flr = mm_d2i(-floor(z.re));
+        for (int n = 0; n < flr; ++n) denom = mm_cd_mul(denom, mm_cd_make(z.re + n, z.im));
+        // the reference recurses on the float-narrowed z + flr
+        float2 zr = mm_c_narrow(mm_cd_make(z.re + flr, z.im));
+        z = mm_cd_of(zr);
+    }
+    mm_cd w = mm_cd_make(z.re - 1.0, z.im), s = mm_cd_make(coeff[0], 0.0), H = mm_cd_make(1.0, 0.0);
+    for (int n = 1; n < 7; n++) {
+        H = mm_cd_mul(H, mm_cd_div(mm_cd_make(w.re + 1 - n, w.im), mm_cd_make(w.re + n, w.im)));
+        s.re += coeff[n] * H.re;
+        s.im += coeff[n] * H.im;
+    }
+    mm_cd e = mm_cd_exp(mm_cd_make(-w.re - 5.5, -w.im));
+    mm_cd base = mm_cd_make(w.re + 5.5, w.im), ex = mm_cd_make(w.re + 0.5, w.im);
+    mm_cd pw = mm_cd_exp(mm_cd_mul(ex, mm_cd_log(base)));
+    mm_cd r = mm_cd_mul(mm_cd_mul(mm_cd_make(2.506628274631 * e.re, 2.506628274631 * e.im), pw), s);
+    float2 g = mm_c_narrow(r);
+    if (zf.x < 0.0f) g = mm_c_narrow(mm_cd_div(mm_cd_of(g), denom));
+    return g;
+}
+
+// ---------------------------------------------------------------------- colours
+// packing R<<24|G<<16|B<<8|A (color.h:36-43); k/255.0 narrowed to float is
+// computed exactly for every k in 0..255 as fma(k, hi, k*lo) with hi+lo = 1/255
+MM_DEV float mm_unit_from_byte(unsigned k) {
+    float f = (float)k;
+    return __fmaf_rn(f, 0.003921568859368563f, __fmul_rn(f, -2.319175823606301e-10f));
+}
+MM_DEV float mm_red(mm_color c) { return mm_unit_from_byte(c >> 24); }
+MM_DEV float mm_green(mm_color c) { return mm_unit_from_byte((c >> 16) & 0xff); }
+MM_DEV float mm_blue(mm_color c) { return mm_unit_from_byte((c >> 8) & 0xff); }
+MM_DEV float mm_alpha(mm_color c) { return mm_unit_from_byte(c & 0xff); }
+MM_DEV mm_tup<4> mm_tuple_from_color(mm_color c) {
+    mm_tup<4> t;
+    t.v[0] = mm_red(c); t.v[1] = mm_green(c); t.v[2] = mm_blue(c); t.v[3] = mm_alpha(c);
+    return t;
+}
+// MAKE_COLOR (opmacros.h:154): float product, truncated, masked
+MM_DEV mm_color mm_make_color(float r, float g, float b, float a) {
+    unsigned R = (unsigned)mm_f2i(__fmul_rn(mm_clamp01(r), 255.0f)) & 0xff, G = (unsigned)mm_f2i(__fmul_rn(mm_clamp01(g), 255.0f)) & 0xff;
+    unsigned B = (unsigned)mm_f2i(__fmul_rn(mm_clamp01(b), 255.0f)) & 0xff, A = (unsigned)mm_f2i(__fmul_rn(mm_clamp01(a), 255.0f)) & 0xff;
+    return (R << 24) | (G << 16) | (B << 8) | A;
+}
+MM_DEV float mm_apply_curve(const float *curve, float p) { return curve[mm_f2i(__fmul_rn(mm_clamp01(p), (float)(MM_CURVE_POINTS - 1)))]; }
+MM_DEV mm_tup<4> mm_apply_gradient(const mm_color *grad, float p) {
+    return mm_tuple_from_color(grad[mm_f2i(__fmul_rn(mm_clamp01(p), (float)(MM_CURVE_POINTS - 1)))]);
+}
+
+// --------------------------------------------------------------------- sampling
+template <int MODE_X, int MODE_Y> MM_DEV void mm_apply_edge_behaviour(int &x, int &y, int width, int height) {
+    // builtins/builtins.c:41-119 (C remainder semantics == CUDA's)
+    if (MODE_X == 1) { if (x < 0) x = x % width + width; else if (x >= width) x %= width; }
+    else if (MODE_X == 2) { if (x < 0) x = -x % width; else if (x >= width) x = (width - 1) - (x % width); }
+    else if (MODE_X == 3) {
+        if (x < 0) { x = -x % width; y = (height - 1) - y; }
+        else if (x >= width) { x = (width - 1) - (x % width); y = (height - 1) - y; }
+    }
+    if (MODE_Y == 1) { if (y < 0) y = y % height + height; else if (y >= height) y %= height; }
+    else if (MODE_Y == 2) { if (y < 0) y = -y % height; else if (y >= height) y = (height - 1) - (y % height); }
+    else if (MODE_Y == 3) {
+        if (y < 0) { x = (width - 1) - x; y = -y % height; }
+        else if (y >= height) { x = (width - 1) - x; y = (height - 1) - (y % height); }
+    }
+}
+
+// one texel as packed colour; out of image -> edge colour (x tested first), frame out of range -> white
+MM_DEV mm_color mm_get_pixel(const mm_params &P, const mm_image &img, int x, int y, int frame) {
+    mm_apply_edge_behaviour<MM_EDGE_X, MM_EDGE_Y>(x, y, img.w, img.h);
+    if (x < 0 || x >= img.w) return P.edge_color_x;
+    if (y < 0 || y >= img.h) return P.edge_color_y;
+    if (frame < 0 || frame >= img.num_frames) return 0xffffffffu;
+    // RGBA8 little-endian word: R in the low byte; swap to R-high packing
+    unsigned w = __ldg((const unsigned *)img.data + ((size_t)y * (size_t)img.w + (size_t)x));
+    return __byte_perm(w, 0, 0x0123);
+}
+
+MM_DEV mm_color mm_sample_nearest(const mm_params &P, const mm_image &img, float x, float y, int frame) {
+    x = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
+    y = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
+#if !MM_SUPERSAMPLING
+    x = __fadd_rn(x, 0.5f);  // x += 0.5 in double then narrowed == float add
+    y = __fadd_rn(y, 0.5f);
+#endif
+    return mm_get_pixel(P, img, mm_f2i(floorf(x)), mm_f2i(floorf(y)), frame);
+}
+
+// bilinear, exactly as builtins.c:165-245 + color.h:48-54: float weights, per
+// channel ((c1*p1 + c2*p2) + c3*p3) + c4*p4 with every op rounded, then rintf to 8 bits
+MM_DEV mm_color mm_sample_bilinear(const mm_params &P, const mm_image &img, float x, float y, int frame) {
+    x = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
+    y = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
+    int x1 = mm_f2i(floorf(x)), y1 = mm_f2i(floorf(y));
+    int x2 = x1 + 1, y2 = y1 + 1;
+    float x2f = __fsub_rn(x, (float)x1), y2f = __fsub_rn(y, (float)y1);
+    float x1f = __fsub_rn(1.0f, x2f), y1f = __fsub_rn(1.0f, y2f);
+    float p1 = __fmul_rn(x1f, y1f), p2 = __fmul_rn(x1f, y2f), p3 = __fmul_rn(x2f, y1f), p4 = __fmul_rn(x2f, y2f);
+    mm_color c1 = mm_get_pixel(P, img, x1, y1, frame), c2 = mm_get_pixel(P, img, x1, y2, frame);
+    mm_color c3 = mm_get_pixel(P, img, x2, y1, frame), c4 = mm_get_pixel(P, img, x2, y2, frame);
+    mm_color result = 0;
+#pragma unroll
+    for (int sh = 24; sh >= 0; sh -= 8) {
+        float a = (float)((c1 >> sh) & 0xff), b = (float)((c2 >> sh) & 0xff), c = (float)((c3 >> sh) & 0xff), d = (float)((c4 >> sh) & 0xff);
+        float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, p1), __fmul_rn(b, p2)), __fmul_rn(c, p3)), __fmul_rn(d, p4));
+        // (color_t)rintf(s) & 0xff: round half to even, then the x86 cast semantics
+        unsigned q = (unsigned)mm_f2i(rintf(s)) & 0xff;
+        result |= q << sh;
+    }
+    return result;
+}
+
+// get_floatmap_pixel, builtins.c:249-265: nearest via lrintf (round half even)
+MM_DEV mm_tup<4> mm_floatmap_pixel(const mm_image &img, float x, float y) {
+    mm_tup<4> t;
+    float fx = __fadd_rn(__fmul_rn(img.ax, x), img.bx), fy = __fadd_rn(__fmul_rn(img.ay, y), img.by);
+    int ix = mm_f2i(rintf(fx)), iy = mm_f2i(rintf(fy));
+    if (ix < 0 || ix >= img.w || iy < 0 || iy >= img.h) { t.v[0] = t.v[1] = t.v[2] = t.v[3] = 0.0f; return t; }
+    float4 v = __ldg((const float4 *)img.data + ((size_t)iy * (size_t)img.w + (size_t)ix));
+    t.v[0] = v.x; t.v[1] = v.y; t.v[2] = v.z; t.v[3] = v.w;
+    return t;
+}
+
+// ORIG_VAL (opmacros.h:199-216); closures never reach here (inlined or called directly)
+MM_DEV mm_tup<4> mm_orig_val(const mm_params &P, int image, float x, float y, float t) {
+    const mm_image &img = P.images[image];
+    x = __fmul_rn(x, img.xf);  // 1.0 unless a RESIZE wrapper survived to run time
+    y = __fmul_rn(y, img.yf);
+    if (img.kind == MM_IMAGE_FLOATMAP) return mm_floatmap_pixel(img, x, y);
+    int frame = mm_f2i(t);
+#if MM_AA
+    return mm_tuple_from_color(mm_sample_bilinear(P, img, x, y, frame));
+#else
+    return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, frame));
+#endif
+}
+// the nearest sampler regardless of MM_AA: render_image of a drawable (builtins.c:306)
+MM_DEV mm_tup<4> mm_orig_val_nearest(const mm_params &P, const mm_image &img, float x, float y) {
+    return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, 0));
+}
+
+// ----------------------------------------------------------------------- output
+// new_template.c.in:272-293: clamp, times 255.0 in double, truncate
+MM_DEV unsigned mm_quant(float v) { return __float2uint_rz(__fmul_rz(mm_clamp01(v), 255.0f)); }
+
+MM_DEV void mm_store_pixel(const mm_params &P, int row, int col, const mm_tup<4> &t) {
+    char *rowp = (char *)P.out + (size_t)(row - P.first_row) * (size_t)P.out_stride;
+    if (P.floatmap) {
+        ((float4 *)rowp)[col] = make_float4(t.v[0], t.v[1], t.v[2], t.v[3]);
+        return;
+    }
+    if (P.bpp == 4) {
+        unsigned w = mm_quant(t.v[0]) | (mm_quant(t.v[1]) << 8) | (mm_quant(t.v[2]) << 16) | (mm_quant(t.v[3]) << 24);
+        ((unsigned *)rowp)[col] = w;
+        return;
+    }
+    unsigned char *p = (unsigned char *)rowp + (size_t)col * P.bpp;
+    if (P.bpp == 3) {
+        p[0] = mm_quant(t.v[0]); p[1] = mm_quant(t.v[1]); p[2] = mm_quant(t.v[2]);
+    } else {
+        double l = ((double)mm_clamp01(t.v[0]) * 0.299 + (double)mm_clamp01(t.v[1]) * 0.587 + (double)mm_clamp01(t.v[2]) * 0.114) * 255.0;
+        p[0] = (unsigned char)mm_d2i(l);
+        if (P.bpp == 2) p[1] = mm_quant(t.v[3]);
+    }
+}
+
+#include "mm_noise.cuh"

@@ -1,0 +1,42 @@
+// Plain structs shared by host code and device code (NVRTC and nvcc).
+#pragma once
+
+#define MM_MAX_IMAGES 16
+#define MM_CURVE_POINTS 1024
+
+typedef unsigned int mm_color;
+
+enum { MM_IMAGE_DRAWABLE = 0, MM_IMAGE_FLOATMAP = 1 };
+
+// One input or intermediate image.  Drawables are RGBA8 (R first); floatmaps are
+// float4 per pixel (reference drawable.h:92-125, floatmap.c:30-47).
+struct mm_image {
+    const void *data;
+    int kind;
+    int w, h;
+    int num_frames;
+    float sx, sy, mx, my;  // drawable: scale and middle (userval.c:263-279)
+    float ax, bx, ay, by;  // floatmap: pixel = a * coord + b
+    float xf, yf;          // resize factors applied to sampling coordinates (opmacros.h:203-207)
+    int pad0, pad1;
+};
+
+// Per-launch parameters (the invocation / frame / slice fields calc_lines reads,
+// reference mathmap.h:161-227, new_template.c.in:210-234).
+struct mm_params {
+    void *out;                // first row of the band
+    long long out_stride;     // bytes per output row
+    const float *xs;          // virtual x per absolute column (CALC_VIRTUAL_X evaluated on the host in double)
+    const float *ys;          // virtual y per absolute row
+    int region_x, region_y, region_w;
+    int first_row, num_rows;  // band, in absolute rows
+    int img_w, img_h, render_w, render_h;
+    int frame;
+    float t;
+    float R;
+    int bpp;
+    int floatmap;
+    mm_color edge_color_x, edge_color_y;
+    mm_image images[MM_MAX_IMAGES];
+};
+
