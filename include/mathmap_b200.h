@@ -63,7 +63,7 @@ int mmb_set_antialiasing(mmb_invocation *inv, int enabled);   /* invocation_set_
 int mmb_set_supersampling(mmb_invocation *inv, int enabled);  /* invocation->supersampling (-o flag) */
 int mmb_set_edge_behaviour(mmb_invocation *inv, int mode_x, int mode_y, uint32_t color_x, uint32_t color_y);
 int mmb_set_output_bpp(mmb_invocation *inv, int bpp);         /* invocation->output_bpp: 1, 2, 3 or 4 */
-int mmb_set_precise_math(mmb_invocation *inv, int enabled);   /* 1: libm calls in double like the host; 0 (default): CUDA float libm */
+int mmb_set_precise_math(mmb_invocation *inv, int enabled);   /* 1 (default): libm calls evaluated in double and narrowed, like the host; 0: CUDA float libm (<= 2 ulp, faster) */
 
 /* userval bindings, reference userval.h userval_t / mathmap_cmdline.c:756-796 (-D name=value) */
 int mmb_set_userval_int(mmb_invocation *inv, int index, int value);

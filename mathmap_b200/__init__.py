@@ -129,7 +129,7 @@ class Module:
 class Invocation:
     """reference: mathmap_invocation_t from invoke_mathmap (mathmap_common.c:747)."""
 
-    def __init__(self, module, width, height, device=0, antialiasing=False, supersampling=False, precise=False, warp_width=None):
+    def __init__(self, module, width, height, device=0, antialiasing=False, supersampling=False, precise=True, warp_width=None):
         self.module = module
         self.width, self.height = width, height
         self.bpp = 4
@@ -236,7 +236,7 @@ class Invocation:
 
 
 def render_file(path, width=None, height=None, uservals=None, t=0.0, frame=0, antialiasing=True, supersampling=False, device=0,
-                precise=False):
+                precise=True):
     """Convenience mirror of `mathmap [-i] [-o] -f script.mm [-s WxH] [-Dname=value ...]`: returns uint8 [H, W, 4].
     The size defaults to that of the first image argument (mathmap_cmdline.c:717-752)."""
     m = Module.from_file(path)

@@ -399,7 +399,9 @@ void pack_frame(mmb_invocation *inv, const FilterKernel &k, Replay &rp, FrameDat
     std::map<int, int> slot_of;
     for (const UniformField &u : k.uniforms) {
         auto it = rp.env.find(u.value);
-        if (it == rp.env.end()) fail("internal error: uniform value was not computed by the host replay");
+        // a frame-constant value defined in the branch of a frame-constant `if` the host did not take
+        // is never read by the device either (same branch): leave it zero
+        if (it == rp.env.end()) continue;
         const HVal &v = it->second;
         unsigned char *dst = fd.uniforms.data() + u.offset;
         switch (u.type) {
