@@ -63,6 +63,7 @@ int mmb_set_antialiasing(mmb_invocation *inv, int enabled);   /* invocation_set_
 int mmb_set_supersampling(mmb_invocation *inv, int enabled);  /* invocation->supersampling (-o flag) */
 int mmb_set_edge_behaviour(mmb_invocation *inv, int mode_x, int mode_y, uint32_t color_x, uint32_t color_y);
 int mmb_set_output_bpp(mmb_invocation *inv, int bpp);         /* invocation->output_bpp: 1, 2, 3 or 4 */
+int mmb_set_warp_shape(mmb_invocation *inv, int warp_width); /* pixels per warp row in the 32x8 tile: 32 (default), 16 or 8 */
 int mmb_set_precise_math(mmb_invocation *inv, int enabled);   /* 1 (default): libm calls evaluated in double and narrowed, like the host; 0: CUDA float libm (<= 2 ulp, faster) */
 
 /* userval bindings, reference userval.h userval_t / mathmap_cmdline.c:756-796 (-D name=value) */
@@ -92,6 +93,10 @@ int mmb_set_userval_image_device(mmb_invocation *inv, int index, const void *dev
 int mmb_init_frame(mmb_invocation *inv, int frame, float t);
 int mmb_calc_lines(mmb_invocation *inv, int first_row, int last_row, void *q, int floatmap);
 int mmb_calc_lines_device(mmb_invocation *inv, int first_row, int last_row, void *device_q, int floatmap, void *stream);
+/* Row-band sharding across GPUs with load balance (the reference splits one frame into contiguous bands per
+ * thread, mathmap_common.c:991-1003; escape-time filters make contiguous bands unequal): renders the 8-row
+ * blocks b with b % count == phase into device_q, compactly (this rank's k-th block at rows [8k, 8k+8)). */
+int mmb_calc_lines_interleaved_device(mmb_invocation *inv, int phase, int count, void *device_q, void *stream);
 /* Batched entry for frame sharding: renders n frames (frame numbers
  * and t values given) into consecutive W*H*bpp device buffers starting at device_q. */
 int mmb_render_frames_device(mmb_invocation *inv, int n, const int *frames, const float *ts, void *device_q, void *stream);
@@ -107,6 +112,10 @@ const char *mmb_kernel_name(const mmb_invocation *inv);
 int mmb_gaussian_blur_device(int device, const float *device_in, float *device_out, int width, int height, float sigma_h_px,
                              float sigma_v_px, void *stream);
 
+/* NVRTC-compiles the module for sm_100a without needing a GPU (build check); returns cubin bytes or -1 */
+long mmb_module_compile_check(mmb_module *m, int antialiasing, int precise_math);
+/* the IIR coefficients the blur computes on the host: 30 doubles n_p n_m d_p d_m bd_p bd_m (gauss.c:39-115) */
+void mmb_gauss_iir_constants(float std_dev, double *out30);
 const char *mmb_last_error(void);
 const char *mmb_version(void);
 

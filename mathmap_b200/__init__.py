@@ -54,6 +54,7 @@ def lib():
         "mmb_init_frame": (ci, [vp, ci, cf]),
         "mmb_calc_lines": (ci, [vp, ci, ci, vp, ci]), "mmb_calc_lines_device": (ci, [vp, ci, ci, vp, ci, vp]),
         "mmb_render_frames_device": (ci, [vp, ci, vp, vp, vp, vp]),
+        "mmb_calc_lines_interleaved_device": (ci, [vp, ci, ci, vp, vp]),
         "mmb_synchronize": (ci, [vp]), "mmb_launch_count": (ctypes.c_long, [vp]), "mmb_kernel_name": (cc, [vp]),
         "mmb_gaussian_blur_device": (ci, [ci, vp, vp, ci, ci, cf, cf, vp]),
         "mmb_gauss_iir_constants": (None, [cf, vp]),
@@ -210,6 +211,10 @@ class Invocation:
     def calc_lines_device(self, device_ptr, first_row=0, last_row=None, floatmap=False, stream=0):
         last_row = self.height if last_row is None else last_row
         self._ck(lib().mmb_calc_lines_device(self._h, first_row, last_row, device_ptr, int(floatmap), stream))
+
+    def calc_lines_interleaved_device(self, device_ptr, phase, count, stream=0):
+        """8-row blocks b with b % count == phase, stored compactly (row-band sharding across ranks)."""
+        self._ck(lib().mmb_calc_lines_interleaved_device(self._h, phase, count, device_ptr, stream))
 
     def render_frames_device(self, device_ptr, ts, frames=None, stream=0):
         n = len(ts)

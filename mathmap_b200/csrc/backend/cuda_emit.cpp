@@ -389,7 +389,9 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
            << "    mm_pixel_coords(col, row);\n"
            << "    if (col >= P.region_w || row >= P.num_rows) return;\n"
            << "    float x = __ldg(P.xs + (col + P.region_x));\n"
-           << "    float y = __ldg(P.ys + (row + P.first_row));\n"
+           << "    const int arow = mm_actual_row(P, row);\n"
+           << "    if (arow >= P.row_limit) return;\n"
+           << "    float y = __ldg(P.ys + arow);\n"
            << "    mm_tup<4> r = mm_eval_" << name << "(P, U, x, y, P.t, P.frame);\n"
            << "    mm_store_pixel(P, row + P.first_row, col, r);\n"
            << "}\n";

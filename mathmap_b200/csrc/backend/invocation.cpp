@@ -444,6 +444,8 @@ struct LaunchGeom {
     int first_row, num_rows;
     float off_x, off_y;
     int xs_count, ys_count;
+    int interleave = 1, phase = 0;  // 8-row block interleaving across ranks (see mm_actual_row)
+    int row_limit = -1;
 };
 
 void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, const LaunchGeom &g, void *out, long long out_stride, int floatmap,
@@ -465,6 +467,9 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     P.region_w = g.region_w;
     P.first_row = g.first_row;
     P.num_rows = g.num_rows;
+    P.row_interleave = g.interleave;
+    P.row_phase = g.phase;
+    P.row_limit = g.row_limit >= 0 ? g.row_limit : g.first_row + g.num_rows;
     P.img_w = inv->W; P.img_h = inv->H; P.render_w = inv->W; P.render_h = inv->H;
     P.frame = frame;
     P.t = t;
@@ -850,6 +855,34 @@ int mmb_calc_lines_device(mmb_invocation *inv, int first_row, int last_row, void
         if (stream) inv->stream = (cudaStream_t)stream;
         try {
             render_band(inv, first_row, last_row, device_q, floatmap);
+        } catch (...) {
+            inv->stream = saved;
+            throw;
+        }
+        inv->stream = saved;
+    });
+}
+
+// Row-band sharding with load balance: renders the 8-row blocks b of the frame with
+// b % count == phase into device_q, stored compactly (block k of this rank at rows [8k, 8k+8)).
+// Contiguous bands (the reference's split, mathmap_common.c:997-998) are mmb_calc_lines_device.
+int mmb_calc_lines_interleaved_device(mmb_invocation *inv, int phase, int count, void *device_q, void *stream) {
+    if (!inv || !device_q || count < 1 || phase < 0 || phase >= count) { set_error("mmb_calc_lines_interleaved_device: bad arguments"); return -1; }
+    return guarded([&] {
+        set_device(inv);
+        if (!inv->frame_ready) fail("mmb_init_frame must be called before rendering");
+        if (inv->cfg.supersampling) fail("interleaved bands do not support supersampling");
+        int blocks = (inv->H + 7) / 8;
+        int mine = blocks > phase ? (blocks - phase + count - 1) / count : 0;
+        if (mine == 0) return;
+        cudaStream_t saved = inv->stream;
+        if (stream) inv->stream = (cudaStream_t)stream;
+        LaunchGeom g{inv->W, inv->H, 0, inv->W, 0, mine * 8, 0.f, 0.f, inv->W + 1, inv->H + 1};
+        g.interleave = count;
+        g.phase = phase;
+        g.row_limit = inv->H;
+        try {
+            launch_filter(inv, inv->m->main, inv->main_frame, g, device_q, (long long)inv->W * inv->bpp, 0, inv->frame, inv->t);
         } catch (...) {
             inv->stream = saved;
             throw;

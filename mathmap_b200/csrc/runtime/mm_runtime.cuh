@@ -367,6 +367,12 @@ MM_DEV mm_tup<4> mm_orig_val_nearest(const mm_params &P, const mm_image &img, fl
     return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, 0));
 }
 
+// local (compact) row of this launch -> absolute image row
+MM_DEV int mm_actual_row(const mm_params &P, int row) {
+    if (P.row_interleave <= 1) return row + P.first_row;
+    return P.first_row + ((row >> 3) * P.row_interleave + P.row_phase) * 8 + (row & 7);
+}
+
 // ----------------------------------------------------------------------- output
 // new_template.c.in:272-293: clamp, times 255.0 in double, truncate
 MM_DEV unsigned mm_quant(float v) { return __float2uint_rz(__fmul_rz(mm_clamp01(v), 255.0f)); }

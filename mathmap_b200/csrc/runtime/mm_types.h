@@ -29,7 +29,9 @@ struct mm_params {
     const float *xs;          // virtual x per absolute column (CALC_VIRTUAL_X evaluated on the host in double)
     const float *ys;          // virtual y per absolute row
     int region_x, region_y, region_w;
-    int first_row, num_rows;  // band, in absolute rows
+    int first_row, num_rows;  // band, in absolute rows (num_rows counts rendered rows)
+    int row_limit;            // absolute row bound (exclusive)
+    int row_interleave, row_phase;  // > 1: render only 8-row blocks b with b % row_interleave == row_phase, stored compactly
     int img_w, img_h, render_w, render_h;
     int frame;
     float t;

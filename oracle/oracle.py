@@ -44,7 +44,7 @@ class _RenderParams(ctypes.Structure):
                 ("edge_color_x", ctypes.c_uint), ("edge_color_y", ctypes.c_uint), ("output_bpp", ctypes.c_int),
                 ("frame", ctypes.c_int), ("t", ctypes.c_float), ("num_threads", ctypes.c_int), ("floatmap", ctypes.c_int),
                 ("num_uservals", ctypes.c_int), ("uservals", ctypes.POINTER(_Userval)), ("output", ctypes.c_void_p),
-                ("taps", ctypes.c_long)]
+                ("taps", ctypes.c_long), ("sample_rows", ctypes.c_void_p), ("num_sample_rows", ctypes.c_int)]
 
 
 def _run(cmd):
@@ -124,8 +124,9 @@ class OracleFilter:
         return d
 
     def render(self, width, height, uservals=None, t=0.0, frame=0, antialiasing=True, supersampling=False, threads=1,
-               edge_behaviour=(0, 0), edge_colors=(0, 0), bpp=4, floatmap=False):
-        """Renders one frame; returns uint8 [H, W, bpp] (or float32 [H, W, 4] when floatmap)."""
+               edge_behaviour=(0, 0), edge_colors=(0, 0), bpp=4, floatmap=False, sample_rows=None):
+        """Renders one frame; returns uint8 [H, W, bpp] (or float32 [H, W, 4] when floatmap).
+        sample_rows: optional list of row indices; only those rows are rendered (output has len(sample_rows) rows)."""
         vals = self.userval_defaults()
         if uservals:
             for k, v in uservals.items():
@@ -164,10 +165,15 @@ class OracleFilter:
                     keep.append(img)
                     arr[i].v.image = self.lib.mmo_make_drawable(img.ctypes.data, img.shape[1], img.shape[0])
                 drawables.append(arr[i].v.image)
+        rows_arr = None
+        out_rows = height
+        if sample_rows is not None:
+            rows_arr = np.ascontiguousarray(sample_rows, dtype=np.int32)
+            out_rows = len(rows_arr)
         if floatmap:
-            out = np.zeros((height, width, 4), dtype=np.float32)
+            out = np.zeros((out_rows, width, 4), dtype=np.float32)
         else:
-            out = np.zeros((height, width, bpp), dtype=np.uint8)
+            out = np.zeros((out_rows, width, bpp), dtype=np.uint8)
         p = _RenderParams()
         p.img_width, p.img_height = width, height
         p.antialiasing, p.supersampling = int(antialiasing), int(supersampling)
@@ -180,6 +186,9 @@ class OracleFilter:
         p.num_uservals = n
         p.uservals = arr
         p.output = out.ctypes.data
+        if rows_arr is not None:
+            p.sample_rows = rows_arr.ctypes.data
+            p.num_sample_rows = len(rows_arr)
         rc = self.lib.mmo_render(ctypes.byref(p))
         for d in drawables:
             self.lib.mmo_free_drawable(d)

@@ -30,6 +30,8 @@ typedef struct mmo_render_params {
     mmo_userval *uservals;
     void *output; /* u8 [H][W][bpp] or float [H][W][4] */
     long taps;    /* out: drawable samples taken */
+    const int *sample_rows; /* optional: render only these rows (bounded CPU-baseline samples); output has num_sample_rows rows */
+    int num_sample_rows;
 } mmo_render_params;
 
 mmo_image *mmo_make_drawable(const unsigned char *rgba, int width, int height) {
@@ -56,11 +58,22 @@ typedef struct {
     int region_x, region_y, region_width, region_height;
     unsigned char *q;
     int floatmap;
+    const int *sample_rows; /* when set: rows sample_rows[region_y .. region_y+region_height) one by one */
+    size_t row_bytes;
 } band_t;
 
 static void call_invocation(band_t *b) {
     mmo_invocation *inv = b->invocation;
     int W = inv->render_width, H = inv->render_height;
+    if (b->sample_rows) {
+        int i;
+        for (i = 0; i < b->region_height; ++i) {
+            int row = b->sample_rows[b->region_y + i];
+            mmo_main_calc_lines(inv, b->closure, b->xy_vars, b->frame, b->t, W, H, 0, 0, W, H, 0.0f, 0.0f, row, row + 1,
+                                b->q + (size_t)i * b->row_bytes, b->floatmap);
+        }
+        return;
+    }
     if (inv->supersampling && !b->floatmap) {
         int bpp = inv->output_bpp, row, col, i;
         unsigned char *line1 = (unsigned char *)malloc((b->region_width + 1) * bpp);
@@ -107,7 +120,7 @@ int mmo_render(mmo_render_params *p) {
     mmo_pools frame_pools;
     void *xy_vars;
     int i, n = p->num_threads < 1 ? 1 : p->num_threads;
-    int first_row = 0, last_row = p->img_height;
+    int first_row = 0, last_row = p->sample_rows ? p->num_sample_rows : p->img_height;
     band_t *bands;
     pthread_t *threads;
 
@@ -151,6 +164,8 @@ int mmo_render(mmo_render_params *p) {
         b->region_height = first_row + (last_row - first_row) * (i + 1) / n - b->region_y;
         b->q = (unsigned char *)p->output + (size_t)(b->region_y - first_row) * row_bytes;
         b->floatmap = p->floatmap;
+        b->sample_rows = p->sample_rows;
+        b->row_bytes = row_bytes;
     }
     if (n == 1)
         call_invocation(&bands[0]);

@@ -1,0 +1,68 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/*.h declares; render entry points
+fail loudly (no CPU fallback).  CPU only."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import mathmap_b200 as mb
+from conftest import ROOT, filter_source
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mathmap_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mmb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(os.path.join(ROOT, "mathmap_b200", "libmathmap_b200.so"))
+    names = declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, "declared in include/mathmap_b200.h but not exported: %s" % missing
+
+
+def test_python_binding_covers_header():
+    L = mb.lib()
+    for n in declared_symbols():
+        assert getattr(L, n).argtypes is not None, n
+
+
+def test_compile_error_reporting():
+    with pytest.raises(mb.MathMapError) as e:
+        mb.Module(source="filter f (image in)\n  in(xy + q)\nend\n")
+    assert "Undefined variable q" in str(e.value) and str(e.value).startswith("2:")
+    with pytest.raises(mb.MathMapError):
+        mb.Module(source="filter f () 1 end")  # result must be rgba:4
+    with pytest.raises(mb.MathMapError):
+        mb.Module(ir="(not-mmir)")
+
+
+def test_userval_metadata():
+    m = mb.Module(source=filter_source("examples/Render/Mandelbrot.mm"))
+    uv = m.uservals()
+    assert [u[0] for u in uv] == ["pj", "pk", "c1", "ci", "cj", "ck", "num_iterations"]
+    assert uv[-1][1] == mb.USERVAL_INT and uv[-1][2:] == (2.0, 256.0, 32.0)
+    assert uv[0][1] == mb.USERVAL_FLOAT and uv[0][2:] == (-2.0, 2.0, 0.0)
+    assert m.name == "render_mandelbrot"
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    m = mb.Module(source=filter_source("examples/Render/Mandelbrot.mm"))
+    with pytest.raises(mb.MathMapError) as e:
+        mb.Invocation(m, 16, 16)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_nvrtc_compiles_for_sm100a_without_gpu():
+    for script in ["examples/Distorts/Twirl.mm", "examples/Map/Droste.mm", "examples/Map/IFS Functional.mm"]:
+        m = mb.Module(source=filter_source(script))
+        for precise in (False, True):
+            assert m.compile_check(antialiasing=True, precise=precise) > 10000
+    src = mb.Module(source=filter_source("examples/Distorts/Twirl.mm")).cuda_source
+    assert "mm_kernel_twirl" in src and "mm_orig_val" in src and "__grid_constant__" in src

@@ -1,0 +1,80 @@
+"""Front end and IR: language rules that decide what a filter means, IR text round trip, constness levels.  CPU only."""
+import re
+
+import pytest
+
+import mathmap_b200 as mb
+from conftest import filter_source, load_manifest
+
+
+def ir_of(src):
+    return mb.Module(source=src).ir
+
+
+def test_all_fixture_filters_compile_and_round_trip():
+    """mmb_load_ir(mmb_module_ir(m)) reproduces the same IR text: the boundary format is self-consistent."""
+    for e in load_manifest():
+        ir = ir_of(filter_source(e["script"]))
+        again = mb.Module(ir=ir).ir
+        assert again == ir, e["script"]
+
+
+def test_integer_and_float_typing():
+    ir = ir_of("filter f () p = 3; q = p / 2; c = floor(q * 3); grayColor(c % 2) end")
+    # 3/2 is folded as a float division (DIV always yields float), floor gives an int, % is fmod (float)
+    assert "f:1.5" not in ir  # folded further
+    assert re.search(r"\(tuple f:0\.0 f:0\.0 f:0\.0 i:1\)", ir), ir
+
+
+def test_division_by_zero_guard_and_short_circuit_shape():
+    ir = ir_of("filter f (float p: 0-1) grayColor(1 / p) end")
+    assert "(op EQ" in ir and "(op DIV i:1" in ir and "(phi" in ir
+
+
+def test_operator_precedence_and_casts():
+    # unary minus binds tighter than ^ ; cast binds tightest: ri:x*2 is (ri:x)*2
+    a = ir_of("filter f () v = -2 ^ 2; grayColor(v) end")
+    assert "f:4.0" in a
+    with pytest.raises(mb.MathMapError):
+        ir_of("filter f () v = xy:[1,2] + ri:[1,2,3]; grayColor(1) end")
+
+
+def test_variable_typing_errors():
+    with pytest.raises(mb.MathMapError) as e:
+        ir_of("filter f () v = 1; v = [1,2]; grayColor(v) end")
+    assert "two different types" in str(e.value)
+    with pytest.raises(mb.MathMapError) as e:
+        ir_of("filter f () x = 1; grayColor(x) end")
+    assert "internal variable" in str(e.value)
+
+
+def test_for_loop_and_do_while():
+    ir = ir_of("filter f () s = 0; for i = 1 .. 4 do s = s + i end; grayColor(s / 10) end")
+    assert "(while" in ir  # loops are never unrolled; the whole loop is frame-constant (level 0)
+    assert re.search(r"\(while \(phis[^)]*\n\s*\(phi %\d+\.\d+ \d+ 0 ", ir), ir
+    or_ir = ir_of("filter f (int n: 1-10 (3)) s = 0; i = 0; do s = s + i; i = i + 1 while i < n end; grayColor(s) end")
+    assert "(while" in or_ir
+
+
+def test_levels_hoist_frame_constants_and_rows():
+    ir = ir_of(filter_source("examples/Distorts/Sea.mm"))
+    sin_line = [l for l in ir.splitlines() if "(op sin" in l][0]
+    assert re.search(r"\(assign %\d+\.\d+ \d+ 1 \(op sin", sin_line), "sin(t*2*pi + f(y)) is constant along a row"
+    uv_line = [l for l in ir.splitlines() if "USERVAL_FLOAT_ACCESS" in l][0]
+    assert " 7 0 " in uv_line, "uservals are frame constants"
+    orig = [l for l in ir.splitlines() if "ORIG_VAL" in l][0]
+    assert " 0 3 " in orig
+
+
+def test_closure_inlining_and_recursion():
+    src = filter_source("tests/Twice.mm")
+    ir = ir_of(src)
+    assert "(filter " in ir.split("(main")[0]
+    rec = ir_of(filter_source("examples/Map/IFS Functional.mm"))
+    assert re.search(r"\(filter \w+ ", rec.split("(code", 1)[1]), "recursive calls stay calls"
+
+
+def test_native_filter_closure_is_frame_constant():
+    ir = ir_of(filter_source("examples/Blur/Gaussian Blur.mm"))
+    line = [l for l in ir.splitlines() if "(closure gaussian_blur" in l][0]
+    assert re.search(r" 7 0 \(closure gaussian_blur", line)
