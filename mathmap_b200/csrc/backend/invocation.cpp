@@ -107,6 +107,8 @@ struct mmb_invocation {
     void *staging2 = nullptr;
     size_t staging2_bytes = 0;
     void *default_curve = nullptr, *default_gradient = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device->host copies overlap the next chunk's kernel
+    std::vector<cudaEvent_t> chunk_events;
 
     void *alloc(size_t bytes) {
         bytes = (bytes + 255) & ~(size_t)255;
@@ -541,9 +543,8 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
             fail("gaussian blur: unsupported kernel length");
         inv->launches += 2;
     } else {
-        ck(cudaMemcpyAsync(out.data, src.data, bytes, cudaMemcpyDeviceToDevice, inv->stream), "cudaMemcpyAsync(floatmap copy)");
         void *scratch = inv->alloc(gauss_iir_scratch_bytes(src.w, src.h));
-        launch_gauss_iir((float *)out.data, (double *)scratch, src.w, src.h, sh, sv, inv->stream);
+        launch_gauss_iir((const float *)src.data, (float *)out.data, (double *)scratch, src.w, src.h, sh, sv, inv->stream);
         inv->launches += 2;
     }
     ck(cudaGetLastError(), "gaussian blur launch");
@@ -694,6 +695,8 @@ void mmb_invocation_free(mmb_invocation *inv) {
     for (auto &u : inv->uservals)
         if (u.table) cudaFree(u.table);
     for (auto &c : inv->coord_cache) cudaFree(c.second);
+    for (auto e : inv->chunk_events) cudaEventDestroy(e);
+    if (inv->copy_stream) cudaStreamDestroy(inv->copy_stream);
     if (inv->staging) cudaFree(inv->staging);
     if (inv->staging2) cudaFree(inv->staging2);
     if (inv->default_curve) cudaFree(inv->default_curve);
@@ -900,8 +903,29 @@ int mmb_calc_lines(mmb_invocation *inv, int first_row, int last_row, void *q, in
         size_t row_bytes = floatmap ? sizeof(float) * 4 * (size_t)inv->W : (size_t)inv->W * inv->bpp;
         size_t bytes = row_bytes * (size_t)(lr - fr);
         void *d = inv->ensure_staging(inv->staging, inv->staging_bytes, bytes);
-        render_band(inv, fr, lr, d, floatmap);
-        ck(cudaMemcpyAsync(q, d, bytes, cudaMemcpyDeviceToHost, inv->stream), "cudaMemcpyAsync(D2H)");
+        // The band is rendered in chunks; the device->host copy of chunk i runs on a second stream while
+        // the kernel of chunk i+1 runs (q pinned: true overlap; pageable q: still correct).
+        int rows = lr - fr;
+        int chunks = 1;
+        if (!inv->cfg.supersampling && bytes >= ((size_t)8 << 20)) chunks = (int)std::min<size_t>(16, std::max<size_t>(2, bytes >> 25));
+        int chunk_rows = ((rows + chunks - 1) / chunks + 7) & ~7;
+        if (!inv->copy_stream) ck(cudaStreamCreateWithFlags(&inv->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        int ci = 0;
+        for (int r0 = fr; r0 < lr; r0 += chunk_rows, ++ci) {
+            int r1 = std::min(lr, r0 + chunk_rows);
+            char *dchunk = (char *)d + (size_t)(r0 - fr) * row_bytes;
+            render_band(inv, r0, r1, dchunk, floatmap);
+            if ((int)inv->chunk_events.size() <= ci) {
+                cudaEvent_t e;
+                ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+                inv->chunk_events.push_back(e);
+            }
+            ck(cudaEventRecord(inv->chunk_events[ci], inv->stream), "cudaEventRecord");
+            ck(cudaStreamWaitEvent(inv->copy_stream, inv->chunk_events[ci], 0), "cudaStreamWaitEvent");
+            ck(cudaMemcpyAsync((char *)q + (size_t)(r0 - fr) * row_bytes, dchunk, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, inv->copy_stream),
+               "cudaMemcpyAsync(D2H)");
+        }
+        ck(cudaStreamSynchronize(inv->copy_stream), "cudaStreamSynchronize");
         ck(cudaStreamSynchronize(inv->stream), "cudaStreamSynchronize");
     });
 }
@@ -943,8 +967,7 @@ int mmb_gaussian_blur_device(int device, const float *device_in, float *device_o
         } else {
             void *scratch = nullptr;
             ck(cudaMalloc(&scratch, gauss_iir_scratch_bytes(width, height)), "cudaMalloc(scratch)");
-            if (device_out != device_in) ck(cudaMemcpyAsync(device_out, device_in, bytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync");
-            launch_gauss_iir(device_out, (double *)scratch, width, height, sigma_h_px, sigma_v_px, s);
+            launch_gauss_iir(device_in, device_out, (double *)scratch, width, height, sigma_h_px, sigma_v_px, s);
             cudaStreamSynchronize(s);
             cudaFree(scratch);
         }

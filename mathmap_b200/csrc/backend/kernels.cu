@@ -61,54 +61,106 @@ struct GaussCoeffs {
     double n_p[5], n_m[5], d_p[5], d_m[5], bd_p[5], bd_m[5];
 };
 
-__global__ void __launch_bounds__(128) gauss_iir_lines_kernel(float *data, double *scratch, int nlines, int n, long long line_stride,
+// One recursion step.  s[0] is the current sample, s[1..4] the previous four in
+// sweep direction; v[1..4] the previous four outputs.  Order of operations as in
+// gauss.c:182-190: acc += n[i]*s[i] - d[i]*v[i] for i = 0..terms, then the
+// boundary terms (n[j] - bd[j]) * initial for j = terms+1..4.
+__device__ __forceinline__ double iir_step(const double *n, const double *d, const double *bd, double s0, double s1, double s2, double s3, double s4,
+                                           double v1, double v2, double v3, double v4, int terms, double initial) {
+    double acc = 0.0;
+    acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[0], s0), __dmul_rn(d[0], acc)));
+    if (terms >= 4) {  // steady state: no boundary terms
+        acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[1], s1), __dmul_rn(d[1], v1)));
+        acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[2], s2), __dmul_rn(d[2], v2)));
+        acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[3], s3), __dmul_rn(d[3], v3)));
+        acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[4], s4), __dmul_rn(d[4], v4)));
+        return acc;
+    }
+    if (terms >= 1) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[1], s1), __dmul_rn(d[1], v1)));
+    if (terms >= 2) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[2], s2), __dmul_rn(d[2], v2)));
+    if (terms >= 3) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[3], s3), __dmul_rn(d[3], v3)));
+    for (int j = terms + 1; j <= 4; ++j) acc = __dadd_rn(acc, __dmul_rn(__dsub_rn(n[j], bd[j]), initial));
+    return acc;
+}
+
+// Tiles of IIR_T steps: the samples (and, in the causal sweep, the anticausal
+// states) of the NEXT tile are loaded into registers before the current tile's
+// dependent chain of double operations runs, so global-memory latency overlaps
+// the recursion instead of stalling every step.
+#define IIR_T 8
+__global__ void __launch_bounds__(128) gauss_iir_lines_kernel(const float *in, float *out, double *scratch, int nlines, int n, long long line_stride,
                                                               long long elem_stride, long long scratch_line_stride, long long scratch_elem_stride,
                                                               GaussCoeffs C) {
     int tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nlines * 4) return;
     int line = tid >> 2, ch = tid & 3;
-    float *p = data + (size_t)line * line_stride + ch;
+    const float *p = in + (size_t)line * line_stride + ch;
+    float *o = out + (size_t)line * line_stride + ch;
     double *sc = scratch + (size_t)line * scratch_line_stride + ch;
+    const int ntiles = (n + IIR_T - 1) / IIR_T;
 
-    // anticausal: k = n-1 .. 0, uses samples and state to the right
+    // anticausal: k = n-1 .. 0 (step = n-1-k), uses samples and state to the right
     {
-        const float initial = p[(size_t)(n - 1) * elem_stride];
-        double s1 = 0, s2 = 0, s3 = 0, s4 = 0;  // sp_m[1..4]
-        double v1 = 0, v2 = 0, v3 = 0, v4 = 0;  // vm[1..4]
-        for (int k = n - 1, step = 0; k >= 0; --k, ++step) {
-            const double s0 = (double)p[(size_t)k * elem_stride];
-            const int terms = step < 4 ? step : 4;
-            double acc = 0.0;
-            // i = 0: n_m[0] * s0 - d_m[0] * vm[0], vm[0] is still 0 here
-            acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_m[0], s0), __dmul_rn(C.d_m[0], acc)));
-            if (terms >= 1) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_m[1], s1), __dmul_rn(C.d_m[1], v1)));
-            if (terms >= 2) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_m[2], s2), __dmul_rn(C.d_m[2], v2)));
-            if (terms >= 3) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_m[3], s3), __dmul_rn(C.d_m[3], v3)));
-            if (terms >= 4) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_m[4], s4), __dmul_rn(C.d_m[4], v4)));
-            for (int j = terms + 1; j <= 4; ++j) acc = __dadd_rn(acc, __dmul_rn(__dsub_rn(C.n_m[j], C.bd_m[j]), (double)initial));
-            sc[(size_t)k * scratch_elem_stride] = acc;
-            s4 = s3; s3 = s2; s2 = s1; s1 = s0;
-            v4 = v3; v3 = v2; v2 = v1; v1 = acc;
+        const double initial = (double)p[(size_t)(n - 1) * elem_stride];
+        double s1 = 0, s2 = 0, s3 = 0, s4 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+        float cur[IIR_T], nxt[IIR_T];
+#pragma unroll
+        for (int i = 0; i < IIR_T; ++i) { int k = n - 1 - i; nxt[i] = k >= 0 ? p[(size_t)k * elem_stride] : 0.f; }
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int step0 = tile * IIR_T;
+#pragma unroll
+            for (int i = 0; i < IIR_T; ++i) cur[i] = nxt[i];
+            if (tile + 1 < ntiles) {
+#pragma unroll
+                for (int i = 0; i < IIR_T; ++i) { int k = n - 1 - (step0 + IIR_T + i); nxt[i] = k >= 0 ? p[(size_t)k * elem_stride] : 0.f; }
+            }
+#pragma unroll
+            for (int i = 0; i < IIR_T; ++i) {
+                const int step = step0 + i, k = n - 1 - step;
+                if (k >= 0) {
+                    const double s0 = (double)cur[i];
+                    const double acc = iir_step(C.n_m, C.d_m, C.bd_m, s0, s1, s2, s3, s4, v1, v2, v3, v4, step < 4 ? step : 4, initial);
+                    sc[(size_t)k * scratch_elem_stride] = acc;
+                    s4 = s3; s3 = s2; s2 = s1; s1 = s0;
+                    v4 = v3; v3 = v2; v2 = v1; v1 = acc;
+                }
+            }
         }
     }
     // causal: k = 0 .. n-1, then out = (float)(vp + vm)
     {
-        const float initial = p[0];
+        const double initial = (double)p[0];
         double s1 = 0, s2 = 0, s3 = 0, s4 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
-        for (int k = 0; k < n; ++k) {
-            const double s0 = (double)p[(size_t)k * elem_stride];
-            const int terms = k < 4 ? k : 4;
-            double acc = 0.0;
-            acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_p[0], s0), __dmul_rn(C.d_p[0], acc)));
-            if (terms >= 1) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_p[1], s1), __dmul_rn(C.d_p[1], v1)));
-            if (terms >= 2) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_p[2], s2), __dmul_rn(C.d_p[2], v2)));
-            if (terms >= 3) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_p[3], s3), __dmul_rn(C.d_p[3], v3)));
-            if (terms >= 4) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(C.n_p[4], s4), __dmul_rn(C.d_p[4], v4)));
-            for (int j = terms + 1; j <= 4; ++j) acc = __dadd_rn(acc, __dmul_rn(__dsub_rn(C.n_p[j], C.bd_p[j]), (double)initial));
-            const double vm = sc[(size_t)k * scratch_elem_stride];
-            p[(size_t)k * elem_stride] = (float)__dadd_rn(acc, vm);
-            s4 = s3; s3 = s2; s2 = s1; s1 = s0;
-            v4 = v3; v3 = v2; v2 = v1; v1 = acc;
+        float cur[IIR_T], nxt[IIR_T];
+        double curv[IIR_T], nxtv[IIR_T];
+#pragma unroll
+        for (int i = 0; i < IIR_T; ++i) {
+            nxt[i] = i < n ? p[(size_t)i * elem_stride] : 0.f;
+            nxtv[i] = i < n ? sc[(size_t)i * scratch_elem_stride] : 0.0;
+        }
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int k0 = tile * IIR_T;
+#pragma unroll
+            for (int i = 0; i < IIR_T; ++i) { cur[i] = nxt[i]; curv[i] = nxtv[i]; }
+            if (tile + 1 < ntiles) {
+#pragma unroll
+                for (int i = 0; i < IIR_T; ++i) {
+                    int k = k0 + IIR_T + i;
+                    nxt[i] = k < n ? p[(size_t)k * elem_stride] : 0.f;
+                    nxtv[i] = k < n ? sc[(size_t)k * scratch_elem_stride] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < IIR_T; ++i) {
+                const int k = k0 + i;
+                if (k < n) {
+                    const double s0 = (double)cur[i];
+                    const double acc = iir_step(C.n_p, C.d_p, C.bd_p, s0, s1, s2, s3, s4, v1, v2, v3, v4, k < 4 ? k : 4, initial);
+                    o[(size_t)k * elem_stride] = (float)__dadd_rn(acc, curv[i]);
+                    s4 = s3; s3 = s2; s2 = s1; s1 = s0;
+                    v4 = v3; v3 = v2; v2 = v1; v1 = acc;
+                }
+            }
         }
     }
 }
@@ -147,20 +199,20 @@ void gauss_iir_constants_host(float std_dev, double *out30) {
 
 size_t gauss_iir_scratch_bytes(int width, int height) { return sizeof(double) * 4 * (size_t)width * height; }
 
-// data: float4 [height][width], blurred in place; scratch: gauss_iir_scratch_bytes()
-void launch_gauss_iir(float *data, double *scratch, int width, int height, float sigma_h, float sigma_v, cudaStream_t stream) {
+// in -> out (float4 [height][width]; may alias); scratch: gauss_iir_scratch_bytes()
+void launch_gauss_iir(const float *in, float *out, double *scratch, int width, int height, float sigma_h, float sigma_v, cudaStream_t stream) {
     GaussCoeffs c;
     // vertical pass: lines are columns
     find_iir_constants(c, sigma_v);
     {
         int threads = width * 4;
-        gauss_iir_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(data, scratch, width, height, 4, (long long)width * 4, 4, (long long)width * 4, c);
+        gauss_iir_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(in, out, scratch, width, height, 4, (long long)width * 4, 4, (long long)width * 4, c);
     }
-    // horizontal pass: lines are rows
+    // horizontal pass: lines are rows, in place on `out`
     find_iir_constants(c, sigma_h);
     {
         int threads = height * 4;
-        gauss_iir_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(data, scratch, height, width, (long long)width * 4, 4, (long long)width * 4, 4, c);
+        gauss_iir_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(out, out, scratch, height, width, (long long)width * 4, 4, (long long)width * 4, 4, c);
     }
 }
 

@@ -338,6 +338,80 @@ MM_DEV mm_color mm_sample_bilinear(const mm_params &P, const mm_image &img, floa
     return result;
 }
 
+// ---- interior fast paths -------------------------------------------------------
+// When every texel a sample touches lies inside the image (the common case) the
+// generic path's per-texel edge handling, 64-bit addressing and int<->float
+// conversions (I2F/F2I issue on the quarter-rate XU pipe) are replaced by:
+//   * one float range test per axis (NaN and out-of-range fall to the generic path),
+//   * byte -> float through PRMT into the mantissa of 2^23 (exact),
+//   * rintf + (int) through the 1.5 * 2^23 magic constant (round half to even, exact for 0..255),
+//   * byte/255 from the rounded float directly.
+// Results are bit-identical to the generic path.
+#define MM_MAGIC_ROUND 12582912.0f  /* 1.5 * 2^23 */
+MM_DEV float mm_byte_as_float(unsigned word, unsigned sel /* 0x7650 | byte index */) {
+    return __fsub_rn(__int_as_float(__byte_perm(word, 0x4B000000u, sel)), 8388608.0f);
+}
+MM_DEV float mm_unit_from_rounded(float qf) {  // qf holds an integer 0..255 exactly
+    return __fmaf_rn(qf, 0.003921568859368563f, __fmul_rn(qf, -2.319175823606301e-10f));
+}
+// floor of a float known to be in [0, 2^22): no conversion instructions
+MM_DEV float mm_floor_small_nonneg(float v) {
+    float r = __fsub_rn(__fadd_rn(v, 8388608.0f), 8388608.0f);  // nearest integer
+    return r > v ? __fsub_rn(r, 1.0f) : r;
+}
+
+MM_DEV bool mm_bilinear_interior(const mm_params &P, const mm_image &img, float x, float y, int frame, mm_tup<4> &out) {
+#if MM_EDGE_X == 0 && MM_EDGE_Y == 0
+    const float px = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
+    const float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
+    // x1 = floor(px) in [0, w-2] and y1 in [0, h-2]  <=>  0 <= px < w-1 and 0 <= py < h-1 (w, h < 2^22)
+    const float wm1 = (float)(img.w - 1), hm1 = (float)(img.h - 1);
+    if (!(px >= 0.0f && px < wm1 && py >= 0.0f && py < hm1 && img.w < (1 << 22) && img.h < (1 << 22) && (unsigned)frame < (unsigned)img.num_frames))
+        return false;
+    const float fx = mm_floor_small_nonneg(px), fy = mm_floor_small_nonneg(py);
+    const unsigned x1 = (unsigned)__float_as_int(__fadd_rn(fx, 8388608.0f)) & 0x7fffffu;
+    const unsigned y1 = (unsigned)__float_as_int(__fadd_rn(fy, 8388608.0f)) & 0x7fffffu;
+    const float x2f = __fsub_rn(px, fx), y2f = __fsub_rn(py, fy);
+    const float x1f = __fsub_rn(1.0f, x2f), y1f = __fsub_rn(1.0f, y2f);
+    const float p1 = __fmul_rn(x1f, y1f), p2 = __fmul_rn(x1f, y2f), p3 = __fmul_rn(x2f, y1f), p4 = __fmul_rn(x2f, y2f);
+    const unsigned *row0 = (const unsigned *)img.data + (y1 * (unsigned)img.w + x1);
+    const unsigned *row1 = row0 + img.w;
+    const unsigned t1 = __ldg(row0), t3 = __ldg(row0 + 1), t2 = __ldg(row1), t4 = __ldg(row1 + 1);  // pixel1..4 of builtins.c:221-224
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // memory byte k is R, G, B, A
+        const unsigned sel = 0x7650u | (unsigned)k;
+        const float a = mm_byte_as_float(t1, sel), b = mm_byte_as_float(t2, sel), c = mm_byte_as_float(t3, sel), d = mm_byte_as_float(t4, sel);
+        const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, p1), __fmul_rn(b, p2)), __fmul_rn(c, p3)), __fmul_rn(d, p4));
+        const float qf = __fsub_rn(__fadd_rn(s, MM_MAGIC_ROUND), MM_MAGIC_ROUND);  // rintf(s), 0 <= s < 256
+        out.v[k] = mm_unit_from_rounded(qf);
+    }
+    return true;
+#else
+    return false;
+#endif
+}
+
+MM_DEV bool mm_nearest_interior(const mm_params &P, const mm_image &img, float x, float y, int frame, mm_tup<4> &out) {
+#if MM_EDGE_X == 0 && MM_EDGE_Y == 0
+    float px = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
+    float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
+#if !MM_SUPERSAMPLING
+    px = __fadd_rn(px, 0.5f);
+    py = __fadd_rn(py, 0.5f);
+#endif
+    if (!(px >= 0.0f && px < (float)img.w && py >= 0.0f && py < (float)img.h && img.w < (1 << 22) && img.h < (1 << 22) && (unsigned)frame < (unsigned)img.num_frames))
+        return false;
+    const unsigned x1 = (unsigned)__float_as_int(__fadd_rn(mm_floor_small_nonneg(px), 8388608.0f)) & 0x7fffffu;
+    const unsigned y1 = (unsigned)__float_as_int(__fadd_rn(mm_floor_small_nonneg(py), 8388608.0f)) & 0x7fffffu;
+    const unsigned t = __ldg((const unsigned *)img.data + (y1 * (unsigned)img.w + x1));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out.v[k] = mm_unit_from_rounded(mm_byte_as_float(t, 0x7650u | (unsigned)k));
+    return true;
+#else
+    return false;
+#endif
+}
+
 // get_floatmap_pixel, builtins.c:249-265: nearest via lrintf (round half even)
 MM_DEV mm_tup<4> mm_floatmap_pixel(const mm_image &img, float x, float y) {
     mm_tup<4> t;
@@ -356,9 +430,12 @@ MM_DEV mm_tup<4> mm_orig_val(const mm_params &P, int image, float x, float y, fl
     y = __fmul_rn(y, img.yf);
     if (img.kind == MM_IMAGE_FLOATMAP) return mm_floatmap_pixel(img, x, y);
     int frame = mm_f2i(t);
+    mm_tup<4> r;
 #if MM_AA
+    if (mm_bilinear_interior(P, img, x, y, frame, r)) return r;
     return mm_tuple_from_color(mm_sample_bilinear(P, img, x, y, frame));
 #else
+    if (mm_nearest_interior(P, img, x, y, frame, r)) return r;
     return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, frame));
 #endif
 }
