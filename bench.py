@@ -39,7 +39,12 @@ WORKLOADS = {
               "Blur/Gaussian Blur.mm -i -Ddev=0.0078134 (sigma 32 px), synthetic 8192x8192 RGBA8 input"),
     "sea": ("Distorts/Sea.mm", 3840, 2160, {}, True, 240, "Distorts/Sea.mm -i, synthetic 3840x2160 RGBA8 input, 240 frames t=f/240"),
 }
-MANDELBROT_FLOPS_PER_ITERATION = 45  # 20 MUL + 19 ADD + 6 NEG in the optimised IR, no FMA credit
+# Optimised IR per loop iteration: 20 MUL + 19 ADD (+ 6 NEG, which are operand sign modifiers in SASS, not instructions,
+# + 1 SQRT that the emitter removes exactly: sqrt(s) < 2 <=> s < 4 for correctly rounded sqrt).  No FMA credit:
+# --fmad=false is required for bit parity.  SURVEY.md section 8d counts 45 (with the NEGs); 39 is the instruction-level figure.
+MANDELBROT_FLOPS_PER_ITERATION = 39
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full captures, profiles/r01_*_ncu_full.txt
+NCU_TRAFFIC_BYTES = {"mandelbrot": 6.96e6 + 1.0171e9, "twirl": 241.8e6 + 229.4e6, "droste": 212.1e6 + 224.0e6}
 B200_SMS, FP32_LANES_PER_SM = 148, 128
 
 
@@ -303,15 +308,17 @@ def main():
             if iters is not None:
                 achieved = MANDELBROT_FLOPS_PER_ITERATION * iters / (kernel_ms / 1e3) / 1e12
                 line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                                    "traffic": None,
+                                    "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
                                     "note": "non-FMA FP32 issue roofline: 148 SMs x 128 lanes x %.0f MHz (median SM clock under load); "
-                                            "45 flops/iteration x %d iterations per launch; output writes are %.1f GB/s of the %s %.0f GB/s HBM peak"
+                                            "39 flops (20 MUL + 19 ADD) per iteration x %d iterations per launch; output writes are %.1f GB/s of the %s %.0f GB/s HBM peak; "
+                                            "traffic = DRAM bytes per launch from profiles/r01_mandelbrot_ncu_full.txt (algorithmic: 1.074e9 output bytes)"
                                             % (sm_mhz, iters, W * H * 4 / (kernel_ms / 1e3) / 1e9, hbm_src, hbm_peak)}
         else:
             bytes_per_px = {"twirl": 8, "droste": 8, "gauss": 40, "sea": 4}[args.workload]
             px = W * H * (len(my_frames) if frames > 1 else 1) / (1 if frames > 1 else world)
             achieved = bytes_per_px * px / (kernel_ms / 1e3) / 1e9
-            line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                                "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
                                 "note": "%d algorithmic bytes/pixel (SURVEY.md section 8d); peak is %s; %d launches per step" % (bytes_per_px, hbm_src, launches_per_step)}
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region

@@ -33,6 +33,49 @@ std::string float_literal(float f) {
     return s + "f";
 }
 
+// ---- exact strength reduction: LESS/LEQ(sqrt(x), c) with x provably >= 0 or NaN ----
+// sqrt is correctly rounded, hence monotonic: sqrt_rn(x) < c  <=>  x < t where t is the smallest
+// float with sqrt_rn(t) >= c (found by stepping floats around c*c on the host); similarly for <=.
+// The result is bit-identical and removes the IEEE square root from escape-time loops (abs(z) < 2).
+bool nonneg_or_nan(const Primary &p, int depth = 0) {
+    if (p.is_const) return (p.c.type == T_INT && p.c.i >= 0) || (p.c.type == T_FLOAT && p.c.f >= 0.0f);
+    const Value *v = p.value;
+    if (v->index < 0 || !v->def || depth > 12) return false;
+    const Stmt *d = v->def;
+    if (d->kind == ST_PHI) return nonneg_or_nan(d->rhs->kind == RHS_PRIMARY ? d->rhs->prim : Primary(), depth + 1) && d->rhs->kind == RHS_PRIMARY &&
+                                  d->rhs2->kind == RHS_PRIMARY && nonneg_or_nan(d->rhs2->prim, depth + 1) && false;  // phis may cycle: be conservative
+    if (d->kind != ST_ASSIGN) return false;
+    const Rhs *r = d->rhs;
+    if (r->kind == RHS_PRIMARY) return nonneg_or_nan(r->prim, depth + 1);
+    if (r->kind != RHS_OP) return false;
+    if (v->cv->type != T_FLOAT) return false;
+    switch (r->op->id) {
+    case OP_MUL: {  // x * x
+        const Primary &a = r->args[0], &b = r->args[1];
+        if (!a.is_const && !b.is_const && a.value == b.value) return true;
+        return nonneg_or_nan(a, depth + 1) && nonneg_or_nan(b, depth + 1);
+    }
+    case OP_ADD: return nonneg_or_nan(r->args[0], depth + 1) && nonneg_or_nan(r->args[1], depth + 1);
+    case OP_ABS: case OP_SQRT: case OP_HYPOT: return true;
+    default: return false;
+    }
+}
+// smallest float t with sqrtf(t) >= c (strict) / largest float t with sqrtf(t) <= c (non-strict); c > 0 finite
+bool sqrt_threshold(float c, bool strict, float *out) {
+    if (!(c > 0.0f) || !std::isfinite(c) || c > 1e18f) return false;
+    float t = c * c;
+    if (!std::isfinite(t) || t <= 0.0f) return false;
+    if (strict) {
+        while (sqrtf(t) >= c) t = nextafterf(t, 0.0f);     // now sqrt(t) < c
+        while (sqrtf(t) < c) t = nextafterf(t, INFINITY);  // smallest with sqrt(t) >= c
+    } else {
+        while (sqrtf(t) <= c) t = nextafterf(t, INFINITY);  // now sqrt(t) > c
+        while (sqrtf(t) > c) t = nextafterf(t, 0.0f);       // largest with sqrt(t) <= c
+    }
+    *out = t;
+    return true;
+}
+
 struct Emitter {
     const mmb_module &mod;
     const FilterCode &code;
@@ -41,6 +84,7 @@ struct Emitter {
     std::set<const Value *> uniform_set;
     std::vector<const Value *> uniform_order;
     std::set<const Filter *> &called;  // filters reached through RHS_FILTER
+    std::set<const Stmt *> fused;       // statements already emitted as part of a fused pair
 
     Emitter(const mmb_module &m, const FilterCode &c, bool cf, std::set<const Filter *> &cl) : mod(m), code(c), call_flavour(cf), called(cl) {}
 
@@ -156,8 +200,20 @@ struct Emitter {
         case OP_FLOOR: return fn1("mm_floor");
         case OP_CEIL: return fn1("mm_ceil");
         case OP_EQ: return "(" + A(0) + " == " + A(1) + ")";
-        case OP_LESS: return "(" + A(0) + " < " + A(1) + ")";
-        case OP_LEQ: return "(" + A(0) + " <= " + A(1) + ")";
+        case OP_LESS:
+        case OP_LEQ: {
+            const char *sym = op->id == OP_LESS ? " < " : " <= ";
+            const Primary &l = r->args[0], &c = r->args[1];
+            if (!l.is_const && l.value->index >= 0 && l.value->def && l.value->def->kind == ST_ASSIGN && l.value->def->rhs->kind == RHS_OP &&
+                l.value->def->rhs->op->id == OP_SQRT && l.value->cv->type == T_FLOAT && c.is_const && (c.c.type == T_INT || c.c.type == T_FLOAT) &&
+                on_device(l.value->level)) {
+                const Primary &x = l.value->def->rhs->args[0];
+                float cf = c.c.type == T_INT ? (float)c.c.i : c.c.f, thr;
+                if (ptype(x) == T_FLOAT && nonneg_or_nan(x) && sqrt_threshold(cf, op->id == OP_LESS, &thr))
+                    return "(" + prim(x) + sym + float_literal(thr) + ") /* sqrt(x)" + sym + float_literal(cf) + ", exact */";
+            }
+            return "(" + A(0) + sym + A(1) + ")";
+        }
         case OP_NOT: return "(!" + A(0) + ")";
         case OP_PRINT: case OP_NEWLINE: case OP_START_DEBUG_TUPLE: case OP_SET_DEBUG_TUPLE_DATA: return "0";
         case OP_APPLY_CURVE: return "mm_apply_curve(" + A(0) + ", " + F(1) + ")";
@@ -279,7 +335,23 @@ struct Emitter {
         for (; s; s = s->next) {
             switch (s->kind) {
             case ST_ASSIGN:
-                if (on_device(s->lhs->level)) out << ind << vname(s->lhs) << " = " << rhs_expr(s->rhs, s->lhs->cv) << ";\n";
+                if (!on_device(s->lhs->level) || fused.count(s)) break;
+                // sin(v) and cos(v) of the same value in one block share one range reduction
+                if (s->rhs->kind == RHS_OP && (s->rhs->op->id == OP_SIN || s->rhs->op->id == OP_COS) && s->lhs->cv->type == T_FLOAT) {
+                    const int other = s->rhs->op->id == OP_SIN ? OP_COS : OP_SIN;
+                    const Stmt *mate = nullptr;
+                    for (const Stmt *q = s->next; q; q = q->next)
+                        if (q->kind == ST_ASSIGN && q->rhs->kind == RHS_OP && q->rhs->op->id == other && on_device(q->lhs->level) &&
+                            q->lhs->cv->type == T_FLOAT && !q->rhs->args[0].is_const && !s->rhs->args[0].is_const &&
+                            q->rhs->args[0].value == s->rhs->args[0].value) { mate = q; break; }
+                    if (mate) {
+                        fused.insert(mate);
+                        const Stmt *sn = s->rhs->op->id == OP_SIN ? s : mate, *cs = s->rhs->op->id == OP_SIN ? mate : s;
+                        out << ind << "mm_sincos(" << as_float(s->rhs->args[0]) << ", " << vname(sn->lhs) << ", " << vname(cs->lhs) << ");\n";
+                        break;
+                    }
+                }
+                out << ind << vname(s->lhs) << " = " << rhs_expr(s->rhs, s->lhs->cv) << ";\n";
                 break;
             case ST_IF:
                 if (!(has_device(s->cons) || has_device(s->alt) || has_device(s->exit))) break;

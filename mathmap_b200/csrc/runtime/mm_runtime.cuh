@@ -119,6 +119,16 @@ MM_LIBM1(mm_tanh, tanh)
 MM_LIBM1(mm_asinh, asinh)
 MM_LIBM1(mm_acosh, acosh)
 MM_LIBM1(mm_atanh, atanh)
+MM_DEV void mm_sincos(float a, float &s, float &c) {
+#if MM_PRECISE
+    double ds, dc;
+    sincos((double)a, &ds, &dc);
+    s = (float)ds;
+    c = (float)dc;
+#else
+    sincosf(a, &s, &c);
+#endif
+}
 // GSL's gsl_sf_gamma / gsl_sf_beta are third-party and absent; tgamma/lgamma based (parity unpinned)
 MM_DEV float mm_gamma(float a) { return ((double)a > 171.0) ? 0.0f : (float)tgamma((double)a); }
 MM_DEV float mm_beta(float a, float b) { return (float)exp(lgamma((double)a) + lgamma((double)b) - lgamma((double)a + (double)b)); }
