@@ -2,6 +2,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <set>
 #include <sstream>
 
@@ -79,16 +80,33 @@ bool sqrt_threshold(float c, bool strict, float *out) {
 struct Emitter {
     const mmb_module &mod;
     const FilterCode &code;
-    bool call_flavour;  // true: a __device__ function evaluating everything per call (non-inlined filter calls)
+    // what this emitter instance prints:
+    //   PIXEL_ALL  every device statement (levels 1 and 3) in the pixel kernel
+    //   PIXEL_ONLY level 3 only; row-constant (level 1) values are read from the row pre-kernel's arrays
+    //   ROW        level 1 only: the row pre-kernel (the reference's per-row "x-const" code, new_template.c.in:251-259)
+    //   CALL       a __device__ function evaluating everything per call (non-inlined filter calls)
+    enum Mode { PIXEL_ALL, PIXEL_ONLY, ROW, CALL };
+    Mode mode;
+    bool call_flavour;
     std::ostringstream out;
-    std::set<const Value *> uniform_set;
-    std::vector<const Value *> uniform_order;
+    std::set<const Value *> own_uniform_set, *uniform_set_p = &own_uniform_set;
+    std::vector<const Value *> own_uniform_order, *uniform_order_p = &own_uniform_order;
+    std::set<const Value *> row_export_set;
+    std::vector<const Value *> row_exports;  // level-1 values the pixel kernel reads
     std::set<const Filter *> &called;  // filters reached through RHS_FILTER
     std::set<const Stmt *> fused;       // statements already emitted as part of a fused pair
 
-    Emitter(const mmb_module &m, const FilterCode &c, bool cf, std::set<const Filter *> &cl) : mod(m), code(c), call_flavour(cf), called(cl) {}
+    Emitter(const mmb_module &m, const FilterCode &c, Mode md, std::set<const Filter *> &cl) : mod(m), code(c), mode(md), call_flavour(md == CALL), called(cl) {}
 
-    bool on_device(int level) const { return call_flavour || level >= 1; }
+    bool on_device(int level) const {
+        switch (mode) {
+        case CALL: return true;
+        case PIXEL_ALL: return level >= 1;
+        case PIXEL_ONLY: return level >= 3;
+        case ROW: return level == 1;
+        }
+        return false;
+    }
 
     static std::string vname(const Value *v) { return "v" + std::to_string(v->cv->id) + "_" + std::to_string(v->index); }
     static std::string ctype(const CompVar *cv) {
@@ -118,8 +136,15 @@ struct Emitter {
         const Value *v = p.value;
         if (v->index < 0) return v->cv->type == T_TUPLE ? ctype(v->cv) + "{}" : (v->cv->type == T_COMPLEX ? "make_float2(0.f, 0.f)" : "0");
         if (!on_device(v->level)) {
-            if (uniform_set.insert(v).second) uniform_order.push_back(v);
-            return "U." + vname(v);
+            if (v->level == 0) {
+                if (uniform_set_p->insert(v).second) uniform_order_p->push_back(v);
+                return "U." + vname(v);
+            }
+            if (mode == PIXEL_ONLY && v->level == 1) {  // loaded from the row arrays at kernel entry
+                if (row_export_set.insert(v).second) row_exports.push_back(v);
+                return vname(v);
+            }
+            unsupported("internal error: value of level " + std::to_string(v->level) + " is not visible here");
         }
         return vname(v);
     }
@@ -296,7 +321,7 @@ struct Emitter {
             switch (s->kind) {
             case ST_ASSIGN: case ST_PHI: if (on_device(s->lhs->level)) return true; break;
             case ST_IF: if (has_device(s->cons) || has_device(s->alt) || has_device(s->exit)) return true; break;
-            case ST_WHILE: if (on_device(s->level)) return true; if (has_device(s->body)) return true; break;
+            case ST_WHILE: if (on_device(s->level) && s->level >= 1) return true; if (has_device(s->body)) return true; break;
             default: break;
             }
         }
@@ -355,6 +380,11 @@ struct Emitter {
                 break;
             case ST_IF:
                 if (!(has_device(s->cons) || has_device(s->alt) || has_device(s->exit))) break;
+                if (mode == ROW && s->level > 1) {  // per-pixel condition: only speculated pure row-level definitions live here
+                    emit_stmts(s->cons, ind);
+                    emit_stmts(s->alt, ind);
+                    break;
+                }
                 out << ind << "if (" << rhs_expr(s->cond, nullptr) << ") {\n";
                 emit_stmts(s->cons, ind + "    ");
                 emit_phis(s->exit, 0, ind + "    ");
@@ -364,7 +394,11 @@ struct Emitter {
                 out << ind << "}\n";
                 break;
             case ST_WHILE:
-                if (!on_device(s->level)) break;  // replayed on the host; nothing inside is per-pixel
+                if (!on_device(s->level)) {
+                    // a loop of another level: at most speculated definitions of this level inside
+                    if (mode == ROW && s->level > 1) emit_stmts(s->body, ind);
+                    break;
+                }
                 emit_phis(s->entry, 0, ind);
                 out << ind << "while (" << rhs_expr(s->cond, nullptr) << ") {\n";
                 emit_stmts(s->body, ind + "    ");
@@ -412,18 +446,48 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         if (f->kind != FILTER_MATHMAP) continue;
         const FilterCode *code = m.code_for(f);
         std::string name = sanitize(f->name);
-        Emitter e(m, *code, false, called);
-        // body first (discovers uniforms)
+        // Is a row pre-kernel worth it?  Only when the row-constant slice holds real work (libm, division,
+        // sampling, noise); a couple of multiplies are cheaper to redo per pixel than to store and reload.
+        int row_cost = 0;
+        {
+            std::function<void(const Stmt *)> scan = [&](const Stmt *st) {
+                for (; st; st = st->next) {
+                    if (st->kind == ST_ASSIGN && st->lhs->level == 1 && st->rhs->kind == RHS_OP) {
+                        int id = st->rhs->op->id;
+                        if ((id >= OP_SQRT && id <= OP_BETA) || (id >= OP_C_SQRT && id <= OP_C_GAMMA) || id == OP_ORIG_VAL ||
+                            (id >= OP_LIBNOISE_PERLIN && id <= OP_LIBNOISE_VORONOI) || id == OP_MOD)
+                            row_cost += 20;
+                        else if (id == OP_DIV) row_cost += 4;
+                        else row_cost += 1;
+                    } else if (st->kind == ST_IF) { scan(st->cons); scan(st->alt); }
+                    else if (st->kind == ST_WHILE) { if (st->level == 1) row_cost += 20; scan(st->body); }
+                }
+            };
+            scan(code->first);
+        }
+        const bool use_rows = row_cost >= 20;
+        Emitter e(m, *code, use_rows ? Emitter::PIXEL_ONLY : Emitter::PIXEL_ALL, called);
+        // body first (discovers uniforms and row exports)
         std::vector<const Value *> decls;
         e.collect_decls(code->first, decls);
         e.emit_stmts(code->first, "    ");
         std::string body = e.out.str();
+        Emitter er(m, *code, Emitter::ROW, called);
+        er.uniform_set_p = &e.own_uniform_set;
+        er.uniform_order_p = &e.own_uniform_order;
+        std::vector<const Value *> row_decls;
+        std::string row_body;
+        if (use_rows) {
+            er.collect_decls(code->first, row_decls);
+            er.emit_stmts(code->first, "    ");
+            row_body = er.out.str();
+        }
 
         FilterKernel k;
         k.filter = f;
         k.kernel_name = "mm_kernel_" + name;
         // layout: 8-byte fields first, then 4-byte ones
-        std::vector<const Value *> order = e.uniform_order;
+        std::vector<const Value *> order = e.own_uniform_order;
         std::stable_sort(order.begin(), order.end(), [](const Value *a, const Value *b) {
             auto big = [](const Value *v) { return v->cv->type == T_CURVE || v->cv->type == T_GRADIENT || v->cv->type == T_COMPLEX; };
             return big(a) && !big(b);
@@ -447,25 +511,74 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         st << "};\n";
         k.uniforms_size = off;
 
+        // row arrays: one 4-byte array per scalar component of every exported row-constant value
+        auto ncomp = [](const Value *v) {
+            switch (v->cv->type) {
+            case T_COMPLEX: return 2;
+            case T_TUPLE: return std::max(1, v->cv->tuple_len);
+            case T_CURVE: case T_GRADIENT: return -1;
+            default: return 1;
+            }
+        };
+        std::ostringstream rv, rv_load, rv_store;
+        rv << "struct mm_rowvals_" << name << " {\n";
+        if (use_rows) {
+            for (const Value *v : e.row_exports) {
+                int nc = ncomp(v);
+                if (nc < 0) unsupported("row-constant curve/gradient values");
+                k.row_slots += nc;
+                std::string vn = Emitter::vname(v);
+                const char *elt = (v->cv->type == T_INT || v->cv->type == T_IMAGE || v->cv->type == T_NIL) ? "int" : (v->cv->type == T_COLOR ? "unsigned" : "float");
+                for (int c2 = 0; c2 < nc; ++c2) rv << "    " << elt << " *" << vn << "_" << c2 << ";\n";
+                rv_load << "    " << Emitter::ctype(v->cv) << " " << vn << ";\n";
+                if (v->cv->type == T_TUPLE) {
+                    for (int c2 = 0; c2 < nc; ++c2) {
+                        rv_load << "    " << vn << ".v[" << c2 << "] = __ldg(RV." << vn << "_" << c2 << " + row);\n";
+                        rv_store << "    RV." << vn << "_" << c2 << "[row] = " << vn << ".v[" << c2 << "];\n";
+                    }
+                } else if (v->cv->type == T_COMPLEX) {
+                    rv_load << "    " << vn << ".x = __ldg(RV." << vn << "_0 + row); " << vn << ".y = __ldg(RV." << vn << "_1 + row);\n";
+                    rv_store << "    RV." << vn << "_0[row] = " << vn << ".x; RV." << vn << "_1[row] = " << vn << ".y;\n";
+                } else {
+                    rv_load << "    " << vn << " = __ldg(RV." << vn << "_0 + row);\n";
+                    rv_store << "    RV." << vn << "_0[row] = " << vn << ";\n";
+                }
+            }
+        }
+        if (k.row_slots == 0) rv << "    float *mm_unused;\n";
+        rv << "};\n";
+        const bool have_rows = use_rows && k.row_slots > 0;
+        if (have_rows) k.row_kernel_name = "mm_rows_" + name;
+
         std::ostringstream fn;
-        fn << st.str();
-        fn << "static __device__ __forceinline__ mm_tup<4> mm_eval_" << name << "(const mm_params &P, const mm_uniforms_" << name
-           << " &U, float x, float y, float t, int frame) {\n";
-        fn << "    mm_tup<4> mm_ret = mm_tup<4>{};\n";
-        for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
-        fn << body;
-        fn << "    return mm_ret;\n}\n";
+        fn << st.str() << rv.str();
+        if (have_rows) {
+            fn << "extern \"C\" __global__ void __launch_bounds__(256) " << k.row_kernel_name << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
+               << name << " U, const __grid_constant__ mm_rowvals_" << name << " RV) {\n"
+               << "    const int row = blockIdx.x * 256 + threadIdx.x;\n"
+               << "    if (row >= P.num_rows) return;\n"
+               << "    const int arow = mm_actual_row(P, row);\n"
+               << "    if (arow >= P.row_limit) return;\n"
+               << "    const float y = __ldg(P.ys + arow);\n"
+               << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)y;\n";
+            for (const Value *v : row_decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
+            fn << row_body << rv_store.str() << "}\n";
+        }
         fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H) " << k.kernel_name << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
-           << name << " U) {\n"
+           << name << " U, const __grid_constant__ mm_rowvals_" << name << " RV) {\n"
            << "    int col, row;\n"
            << "    mm_pixel_coords(col, row);\n"
            << "    if (col >= P.region_w || row >= P.num_rows) return;\n"
-           << "    float x = __ldg(P.xs + (col + P.region_x));\n"
+           << "    const float x = __ldg(P.xs + (col + P.region_x));\n"
            << "    const int arow = mm_actual_row(P, row);\n"
            << "    if (arow >= P.row_limit) return;\n"
-           << "    float y = __ldg(P.ys + arow);\n"
-           << "    mm_tup<4> r = mm_eval_" << name << "(P, U, x, y, P.t, P.frame);\n"
-           << "    mm_store_pixel(P, row + P.first_row, col, r);\n"
+           << "    const float y = __ldg(P.ys + arow);\n"
+           << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)x; (void)y;\n"
+           << "    mm_tup<4> mm_ret = mm_tup<4>{};\n";
+        if (have_rows) fn << rv_load.str();
+        for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
+        fn << body
+           << "    mm_store_pixel(P, row + P.first_row, col, mm_ret);\n"
            << "}\n";
         bodies.push_back(fn.str());
         src.kernels[f] = k;
@@ -481,7 +594,7 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         const FilterCode *code = m.code_for(f);
         std::string name = sanitize(f->name);
         std::set<const Filter *> more;
-        Emitter e(m, *code, true, more);
+        Emitter e(m, *code, Emitter::CALL, more);
         std::vector<const Value *> decls;
         e.collect_decls(code->first, decls);
         e.emit_stmts(code->first, "    ");

@@ -25,6 +25,8 @@ struct FilterKernel {
     std::string kernel_name;           // extern "C" __global__ entry
     std::vector<UniformField> uniforms;
     size_t uniforms_size = 0;          // sizeof(mm_uniforms_<f>) (>= 4)
+    std::string row_kernel_name;       // row pre-kernel (empty: none); fills `row_slots` 4-byte arrays of num_rows entries
+    int row_slots = 0;
 };
 
 struct CudaModuleSource {

@@ -481,9 +481,20 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     P.edge_color_x = inv->edge_color_x;
     P.edge_color_y = inv->edge_color_y;
     for (int i = 0; i < fd.nslots; ++i) P.images[i] = fd.slots[i];
-    void *params[2] = {&P, (void *)fd.uniforms.data()};
+    // row pre-kernel: row-constant values are computed once per row into 4-byte arrays the pixel kernel reads
+    std::vector<void *> rowvals((size_t)std::max(1, k.row_slots), nullptr);
+    void *params[3] = {&P, (void *)fd.uniforms.data(), (void *)rowvals.data()};
     unsigned gx = (unsigned)((g.region_w + 31) / 32), gy = (unsigned)((g.num_rows + 7) / 8);
     if (gx == 0 || gy == 0) return;
+    auto rit = lm->row_functions.find(f);
+    if (rit != lm->row_functions.end()) {
+        size_t per = ((size_t)g.num_rows * 4 + 255) & ~(size_t)255;
+        char *buf = (char *)inv->alloc(per * (size_t)k.row_slots);
+        for (int i = 0; i < k.row_slots; ++i) rowvals[i] = buf + per * (size_t)i;
+        int rrc = api->launch_kernel(rit->second, (unsigned)((g.num_rows + 255) / 256), 1, 1, 256, 1, 1, 0, inv->stream, params, nullptr);
+        if (rrc != 0) fail("cuLaunchKernel(" + k.row_kernel_name + ") failed: " + api->error_string(rrc));
+        inv->launches++;
+    }
     int rc = api->launch_kernel(lm->functions.at(f), gx, gy, 1, 256, 1, 1, 0, inv->stream, params, nullptr);
     if (rc != 0) fail("cuLaunchKernel(" + k.kernel_name + ") failed: " + api->error_string(rc));
     inv->launches++;

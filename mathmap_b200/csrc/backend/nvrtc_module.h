@@ -42,6 +42,7 @@ DriverApi *driver_api(std::string &err);
 struct LoadedModule {
     void *module = nullptr;
     std::map<const mm::Filter *, void *> functions;
+    std::map<const mm::Filter *, void *> row_functions;  // row pre-kernels (absent when a filter has none)
     ~LoadedModule();
 };
 
