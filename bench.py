@@ -233,13 +233,13 @@ def main():
                 inv.calc_lines_interleaved_device(out.data_ptr(), rank, world)
     else:
         my_frames = sharding.frames_for_rank(frames, rank, world)
-        out = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+        out = torch.empty((len(my_frames), H, W, 4), dtype=torch.uint8, device=dev)  # every frame of this rank is kept
         pixels_per_step_all = W * H * frames
+        my_ts = [f / frames for f in my_frames]  # t = frame / num_frames, mathmap_cmdline.c:835
 
         def step(i):
-            for f in my_frames:
-                inv.init_frame(f, f / frames)
-                inv.calc_lines_device(out.data_ptr(), 0, H)
+            # the batched entry point: one C call renders this rank's frames into consecutive device buffers
+            inv.render_frames_device(out.data_ptr(), my_ts, my_frames)
 
     def barrier():
         if world > 1:

@@ -280,6 +280,9 @@ struct Emitter {
         case OP_USERVAL_INT: case OP_USERVAL_FLOAT: case OP_USERVAL_BOOL: case OP_USERVAL_COLOR:
         case OP_USERVAL_CURVE: case OP_USERVAL_GRADIENT: case OP_USERVAL_IMAGE:
             return userval_access(op->id, r->args[0]);
+        case OP_RAND: return "mm_rand(mm_rng, " + F(0) + ", " + F(1) + ")";
+        case OP_SOLVE_LINEAR_2: return "mm_solve_linear_2(" + A(0) + ", " + A(1) + ")";
+        case OP_SOLVE_LINEAR_3: return "mm_solve_linear_3(" + A(0) + ", " + A(1) + ")";
         case OP_OUTPUT_TUPLE: return "(mm_ret = " + A(0) + ", 0)";
         case OP_STRIP_RESIZE: return A(0);  // device image handles never carry a resize wrapper of their own
         default:
@@ -574,7 +577,8 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
            << "    if (arow >= P.row_limit) return;\n"
            << "    const float y = __ldg(P.ys + arow);\n"
            << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)x; (void)y;\n"
-           << "    mm_tup<4> mm_ret = mm_tup<4>{};\n";
+           << "    mm_tup<4> mm_ret = mm_tup<4>{};\n"
+           << "    unsigned mm_rng = mm_rng_seed(col + P.region_x, arow, P.frame); (void)mm_rng;\n";
         if (have_rows) fn << rv_load.str();
         for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
         fn << body
@@ -613,7 +617,8 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         }
         sig << ", float x, float y, float t)";
         protos << sig.str() << ";\n";
-        calls << sig.str() << " {\n    const int frame = 0;\n    (void)frame;\n    mm_tup<4> mm_ret = mm_tup<4>{};\n";
+        calls << sig.str() << " {\n    const int frame = 0;\n    (void)frame;\n    mm_tup<4> mm_ret = mm_tup<4>{};\n"
+              << "    unsigned mm_rng = mm_rng_seed(__float_as_int(x), __float_as_int(y), __float_as_int(t)); (void)mm_rng;\n";
         for (const Value *v : decls) calls << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
         calls << e.out.str() << "    return mm_ret;\n}\n";
         for (const Filter *g : more)

@@ -133,6 +133,45 @@ MM_DEV void mm_sincos(float a, float &s, float &c) {
 MM_DEV float mm_gamma(float a) { return ((double)a > 171.0) ? 0.0f : (float)tgamma((double)a); }
 MM_DEV float mm_beta(float a, float b) { return (float)exp(lgamma((double)a) + lgamma((double)b) - lgamma((double)a + (double)b)); }
 
+// rand(a, b): the reference draws from glib's global Mersenne twister (g_random_double_range,
+// opmacros.h:127), which is not reproducible across runs or threads; PARITY UNPINNED.  Here: a
+// counter-based generator seeded per pixel (PCG output function), uniform in [a, b).
+MM_DEV unsigned mm_rng_seed(int a, int b, int c) {
+    unsigned h = (unsigned)a * 0x9E3779B1u ^ ((unsigned)b * 0x85EBCA77u + 0x7F4A7C15u) ^ ((unsigned)c * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+MM_DEV float mm_rand(unsigned &state, float a, float b) {
+    state = state * 747796405u + 2891336453u;
+    unsigned w = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+    w = (w >> 22u) ^ w;
+    double u = (double)w * (1.0 / 4294967296.0);
+    return (float)((double)a + ((double)b - (double)a) * u);
+}
+// gsl_linalg_HH_solve (GSL, third-party, absent) solves A x = b by Householder; restated with Cramer's rule in
+// double.  PARITY UNPINNED (no reference test divides by a matrix).  A singular matrix gives 0.
+MM_DEV mm_tup<2> mm_solve_linear_2(mm_tup<4> m, mm_tup<2> v) {
+    double a = m.v[0], b = m.v[1], c = m.v[2], d = m.v[3], det = a * d - b * c;
+    mm_tup<2> r;
+    if (det == 0.0) { r.v[0] = r.v[1] = 0.f; return r; }
+    r.v[0] = (float)(((double)v.v[0] * d - b * (double)v.v[1]) / det);
+    r.v[1] = (float)((a * (double)v.v[1] - (double)v.v[0] * c) / det);
+    return r;
+}
+MM_DEV mm_tup<3> mm_solve_linear_3(mm_tup<9> m, mm_tup<3> v) {
+    double a[9], b[3];
+    for (int i = 0; i < 9; ++i) a[i] = m.v[i];
+    for (int i = 0; i < 3; ++i) b[i] = v.v[i];
+    double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    mm_tup<3> r;
+    if (det == 0.0) { r.v[0] = r.v[1] = r.v[2] = 0.f; return r; }
+    double d0 = b[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (b[1] * a[8] - a[5] * b[2]) + a[2] * (b[1] * a[7] - a[4] * b[2]);
+    double d1 = a[0] * (b[1] * a[8] - a[5] * b[2]) - b[0] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * b[2] - b[1] * a[6]);
+    double d2 = a[0] * (a[4] * b[2] - b[1] * a[7]) - a[1] * (a[3] * b[2] - b[1] * a[6]) + b[0] * (a[3] * a[7] - a[4] * a[6]);
+    r.v[0] = (float)(d0 / det); r.v[1] = (float)(d1 / det); r.v[2] = (float)(d2 / det);
+    return r;
+}
+
 // ---------------------------------------------------------------------- complex
 // float _Complex as float2.  Functions are evaluated in double and narrowed (the
 // host uses glibc's float complex functions, themselves accurate to < 1 ulp).

@@ -196,6 +196,10 @@ float _Complex mmo_cgamma(float _Complex z);
 #define gsl_sf_beta(a, b) mmo_beta((a), (b))
 #define cgamma(z) mmo_cgamma((z))
 
+/* GSL's gsl_linalg_HH_solve is absent: Cramer's rule in double (spec_funcs.c), parity unpinned */
+float *mmo_solve_linear_2(const float *m, const float *v, struct mmo_pools *pools);
+float *mmo_solve_linear_3(const float *m, const float *v, struct mmo_pools *pools);
+
 /* libnoise (noise.c) */
 float libnoise_perlin(int octaves, float persistence, float lacunarity, float x, float y, float z);
 float libnoise_billow(int octaves, float persistence, float lacunarity, float x, float y, float z);
