@@ -227,8 +227,9 @@ struct Replay {
     }
 
     // render_image (builtins/builtins.c:269-345)
-    int render_image(int idx, int width, int height);
+    int render_image(int idx, int width, int height, bool force = false);
     int gaussian_blur(const std::vector<HVal> &args);
+    int fft_native(const std::string &name, const std::vector<HVal> &args);
 
     HVal eval(const Rhs *r, const CompVar *dest) {
         switch (r->kind) {
@@ -259,7 +260,7 @@ struct Replay {
             v.type = T_IMAGE;
             if (r->filter->kind == FILTER_NATIVE) {
                 if (r->filter->name == "gaussian_blur") v.image = gaussian_blur(args);
-                else fail("native filter " + r->filter->name + " is not implemented by the CUDA backend yet");
+                else v.image = fft_native(r->filter->name, args);
                 return v;
             }
             HostImage img;
@@ -501,9 +502,9 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     inv->kernel_name = k.kernel_name;
 }
 
-int Replay::render_image(int idx, int width, int height) {
+int Replay::render_image(int idx, int width, int height, bool force) {
     HostImage src = inv->images.at(idx);
-    if (src.kind == IMG_FLOATMAP) return idx;
+    if (src.kind == IMG_FLOATMAP && !force) return idx;
     HostImage out;
     out.kind = IMG_FLOATMAP;
     out.w = width;
@@ -523,6 +524,11 @@ int Replay::render_image(int idx, int width, int height) {
         pack_frame(inv, k, sub, fd);
         LaunchGeom g{width, height, 0, width, 0, height, 0.f, 0.f, width, height};
         launch_filter(inv, src.filter, fd, g, out.data, (long long)sizeof(float) * 4 * width, 1, 0, 0.0f);
+    } else if (src.kind == IMG_FLOATMAP) {
+        // forced re-render of a floatmap: nearest lookup through get_floatmap_pixel (builtins.c:303-342)
+        launch_floatmap_resample((const float *)src.data, src.w, src.h, src.ax, src.bx, src.ay, src.by, src.xf, src.yf, (float *)out.data, width, height,
+                                 out.ax, out.bx, out.ay, out.by, inv->stream);
+        inv->launches++;
     } else {
         mm_image d = to_device_desc(src);
         launch_drawable_to_floatmap(d, (float *)out.data, width, height, out.ax, out.bx, out.ay, out.by, inv->cfg.edge_x, inv->cfg.edge_y,
@@ -530,6 +536,50 @@ int Replay::render_image(int idx, int width, int height) {
         inv->launches++;
     }
     return add_image(out);
+}
+
+// native_filter_convolve / half_convolve / visualize_fft, native-filters/convolve.c:69-357
+int Replay::fft_native(const std::string &name, const std::vector<HVal> &args) {
+    std::string key = name;
+    for (auto &a : args) {
+        char b[64];
+        snprintf(b, sizeof b, ":%d:%d:%a", a.image, a.i, (double)a.f);
+        key += b;
+    }
+    auto it = inv->native_cache.find(key);
+    if (it != inv->native_cache.end()) return it->second;
+    int in = args[0].image;
+    if (inv->images.at(in).kind != IMG_FLOATMAP) in = render_image(in, inv->W, inv->H, true);
+    HostImage src = inv->images.at(in);
+    HostImage out;
+    out.kind = IMG_FLOATMAP;
+    out.w = src.w;
+    out.h = src.h;
+    out.ax = out.bx = (float)((float)(src.w - 1) / 2.0);
+    out.ay = out.by = (float)((float)(src.h - 1) / 2.0);
+    out.ay = (float)(out.ay * -1.0);
+    out.data = inv->alloc(sizeof(float) * 4 * (size_t)src.w * src.h);
+    std::string err;
+    bool ok;
+    if (name == "visualize_fft") {
+        ok = fft_visualize((const float *)src.data, (float *)out.data, src.w, src.h, as_int(args[1]) != 0, inv->stream, &inv->launches, err);
+    } else if (name == "convolve" || name == "half_convolve") {
+        int fi = args[1].image;
+        const HostImage &f0 = inv->images.at(fi);
+        if (f0.kind != IMG_FLOATMAP || f0.w != src.w || f0.h != src.h) fi = render_image(fi, src.w, src.h, true);
+        HostImage filt = inv->images.at(fi);
+        if (name == "convolve")
+            ok = fft_convolve((const float *)src.data, (const float *)filt.data, (float *)out.data, src.w, src.h, as_int(args[2]) != 0, as_int(args[3]) != 0,
+                              inv->stream, &inv->launches, err);
+        else
+            ok = fft_half_convolve((const float *)src.data, (const float *)filt.data, (float *)out.data, src.w, src.h, as_int(args[2]) != 0, inv->stream,
+                                   &inv->launches, err);
+    } else
+        fail("native filter " + name + " is not implemented");
+    if (!ok) fail(err.empty() ? "FFT native filter failed" : err);
+    int idx = add_image(out);
+    inv->native_cache[key] = idx;
+    return idx;
 }
 
 // native_filter_gaussian_blur, native-filters/gauss.c:643-670

@@ -3,6 +3,7 @@
 #include <cuda_runtime_api.h>
 
 #include <cstddef>
+#include <string>
 
 #include "../runtime/mm_types.h"
 
@@ -16,5 +17,13 @@ bool launch_gauss_rle(const float *in, float *tmp, float *out, int width, int he
 void gauss_iir_constants_host(float std_dev, double *out30);
 void launch_supersample_combine(const unsigned char *shortimg, const unsigned char *longimg, unsigned char *out, int width, int height, int long_rows,
                                 int bpp, cudaStream_t stream);
+
+// fft_natives.cu
+void launch_floatmap_resample(const float *src, int sw, int sh, float sax, float sbx, float say, float sby, float xf, float yf, float *out, int width,
+                              int height, float ax, float bx, float ay, float by, cudaStream_t stream);
+bool fft_convolve(const float *in, const float *filt, float *out, int w, int h, int normalize, int copy_alpha, cudaStream_t stream, long *launches,
+                  std::string &err);
+bool fft_half_convolve(const float *in, const float *mask, float *out, int w, int h, int copy_alpha, cudaStream_t stream, long *launches, std::string &err);
+bool fft_visualize(const float *in, float *out, int w, int h, int ignore_alpha, cudaStream_t stream, long *launches, std::string &err);
 
 }  // namespace mmbackend

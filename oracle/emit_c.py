@@ -80,6 +80,9 @@ class Module:
         # native filters known to the runtime: name -> (C function, [userval field per arg])
         self.natives = {
             "gaussian_blur": ("native_filter_gaussian_blur", ["image", "float_const", "float_const"]),
+            "convolve": ("native_filter_convolve", ["image", "image", "bool_const", "bool_const"]),
+            "half_convolve": ("native_filter_half_convolve", ["image", "image", "bool_const"]),
+            "visualize_fft": ("native_filter_visualize_fft", ["image", "bool_const"]),
         }
 
 

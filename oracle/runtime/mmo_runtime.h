@@ -209,6 +209,11 @@ float libnoise_voronoi(float displacement, float x, float y, float z);
 /* native filters (gauss.c) */
 mmo_image *native_filter_gaussian_blur(mmo_invocation *invocation, mmo_userval *args, mmo_pools *pools);
 
+/* FFT natives (convolve.c) */
+mmo_image *native_filter_convolve(mmo_invocation *invocation, mmo_userval *args, mmo_pools *pools);
+mmo_image *native_filter_half_convolve(mmo_invocation *invocation, mmo_userval *args, mmo_pools *pools);
+mmo_image *native_filter_visualize_fft(mmo_invocation *invocation, mmo_userval *args, mmo_pools *pools);
+
 /* images.c */
 mmo_image *mmo_floatmap_alloc(int width, int height, mmo_pools *pools);
 mmo_image *mmo_floatmap_copy(mmo_image *src, mmo_pools *pools);

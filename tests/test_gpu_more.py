@@ -185,3 +185,35 @@ def test_full_size_gaussian_blur_properties():
     d = np.abs(got - got[::-1]).max()
     assert d <= 1, d
     assert got[H // 2, W // 2, 0] > got[H // 2 + 40, W // 2, 0] > got[H // 2 + 100, W // 2, 0]
+
+
+CONVOLVE = """
+filter conv (image in, image kernel, bool copy_alpha (1))
+  convolved = convolve(in, kernel, 1, copy_alpha);
+  convolved(xy)
+end
+"""
+HALF_CONVOLVE = """
+filter hconv (image in, image mask, bool copy_alpha (1))
+  convolved = half_convolve(in, mask, copy_alpha);
+  convolved(xy)
+end
+"""
+
+
+@pytest.mark.parametrize("size", [(64, 64), (96, 40), (45, 63)], ids=["pow2", "even", "odd"])
+def test_fft_native_filters_match_oracle(size):
+    """convolve / half_convolve / visualize_fft (cuFFT double vs the oracle's plain DFT in double)."""
+    w, h = size
+    img = synthetic_rgba(w, h)
+    yy, xx = np.mgrid[0:h, 0:w]
+    k = np.exp(-(((xx - w // 2) ** 2 + (yy - h // 2) ** 2) / 18.0))
+    kernel = np.zeros((h, w, 4), dtype=np.uint8)
+    kernel[:, :, :3] = (k * 255).astype(np.uint8)[:, :, None]
+    kernel[:, :, 3] = 255
+    for src, uv in [(CONVOLVE, {"in": img, "kernel": kernel, "copy_alpha": 1}), (CONVOLVE, {"in": img, "kernel": kernel, "copy_alpha": 0}),
+                    (HALF_CONVOLVE, {"in": img, "mask": kernel, "copy_alpha": 1}),
+                    ("stretched filter v (stretched image in, bool ignore_alpha (1)) visualize_fft(in, ignore_alpha, xy) end", {"in": img})]:
+        got, want = run_both(src, w, h, uv)
+        exact, le1, mx = compare_u8(got, want)
+        assert le1 >= 99.9 and exact >= 99.0, (src.split()[1], size, exact, le1, mx)

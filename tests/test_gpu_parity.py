@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 MANIFEST = load_manifest()
 # filters the CUDA backend does not implement yet (each raises a clear error): FFT natives, GSL-backed ops, rand
-NOT_YET = {"utilities_visualize_fft.png"}
+NOT_YET = set()
 
 
 def bind(inv_or_none, f_oracle, uservals, img):

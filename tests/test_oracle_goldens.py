@@ -11,7 +11,7 @@ from oracle.oracle import OracleFilter
 
 MANIFEST = load_manifest()
 # FFTW-based native filters are a "next" row: no oracle yet
-UNSUPPORTED = {"utilities_visualize_fft.png"}
+UNSUPPORTED = set()
 # goldens whose residual is libm-version noise in glibc's float/complex functions (<= 2 LSB on < 0.05 % of pixels)
 BIT_EXACT_EXPECTED_MIN = 99.9
 
