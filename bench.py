@@ -37,6 +37,8 @@ WORKLOADS = {
     "droste": ("Map/Droste.mm", 8192, 8192, {}, True, 1, "Map/Droste.mm -i, synthetic 8192x8192 RGBA8 input"),
     "gauss": ("Blur/Gaussian Blur.mm", 8192, 8192, {"dev": 0.0078134}, True, 1,
               "Blur/Gaussian Blur.mm -i -Ddev=0.0078134 (sigma 32 px), synthetic 8192x8192 RGBA8 input"),
+    "ident": ("Utilities/Ident.mm", 8192, 8192, {}, True, 1, "Utilities/Ident.mm -i, synthetic 8192x8192 RGBA8 input"),
+    "invert": ("Colors/Invert.mm", 8192, 8192, {}, False, 1, "Colors/Invert.mm (nearest), synthetic 8192x8192 RGBA8 input"),
     "sea": ("Distorts/Sea.mm", 3840, 2160, {}, True, 240, "Distorts/Sea.mm -i, synthetic 3840x2160 RGBA8 input, 240 frames t=f/240"),
 }
 # Optimised IR per loop iteration: 20 MUL + 19 ADD (+ 6 NEG, which are operand sign modifiers in SASS, not instructions,
@@ -314,7 +316,7 @@ def main():
                                             "traffic = DRAM bytes per launch from profiles/r01_mandelbrot_ncu_full.txt (algorithmic: 1.074e9 output bytes)"
                                             % (sm_mhz, iters, W * H * 4 / (kernel_ms / 1e3) / 1e9, hbm_src, hbm_peak)}
         else:
-            bytes_per_px = {"twirl": 8, "droste": 8, "gauss": 40, "sea": 4}[args.workload]
+            bytes_per_px = {"twirl": 8, "droste": 8, "gauss": 40, "sea": 4, "ident": 8, "invert": 8}[args.workload]
             px = W * H * (len(my_frames) if frames > 1 else 1) / (1 if frames > 1 else world)
             achieved = bytes_per_px * px / (kernel_ms / 1e3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
