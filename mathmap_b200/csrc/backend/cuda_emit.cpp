@@ -43,8 +43,6 @@ bool nonneg_or_nan(const Primary &p, int depth = 0) {
     const Value *v = p.value;
     if (v->index < 0 || !v->def || depth > 12) return false;
     const Stmt *d = v->def;
-    if (d->kind == ST_PHI) return nonneg_or_nan(d->rhs->kind == RHS_PRIMARY ? d->rhs->prim : Primary(), depth + 1) && d->rhs->kind == RHS_PRIMARY &&
-                                  d->rhs2->kind == RHS_PRIMARY && nonneg_or_nan(d->rhs2->prim, depth + 1) && false;  // phis may cycle: be conservative
     if (d->kind != ST_ASSIGN) return false;
     const Rhs *r = d->rhs;
     if (r->kind == RHS_PRIMARY) return nonneg_or_nan(r->prim, depth + 1);

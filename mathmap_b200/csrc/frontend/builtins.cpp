@@ -43,14 +43,6 @@ template <class F> void each(const Ctx &c, F f) {
     for (int i = 0; i < c.nres(); ++i) c.res(i, f(i));
 }
 
-void complex_unary(Module &m, const char *name, const char *impl, int cop) {
-    struct S { static void gen(Gen &, GenArgs &) {} };
-    (void)sizeof(S);
-    // one generator per op id: table of captureless lambdas is not possible with
-    // a runtime op, so dispatch through a switch on the impl name at gen time.
-    (void)m; (void)name; (void)impl; (void)cop;
-}
-
 }  // namespace
 
 // Helpers to register families that differ only by the IR op.
