@@ -50,119 +50,165 @@ void launch_drawable_to_floatmap(const mm_image &img, float *out, int width, int
 }
 
 // ---------------------------------------------------------------- Gaussian IIR
-// One thread owns one line of one channel (a column in the vertical pass, a row
-// in the horizontal pass) and runs the 4th-order recursion in double exactly as
-// gauss.c:175-196: the anticausal sweep first, its per-sample state kept in a
-// double scratch line, then the causal sweep, which adds the two and narrows to
-// float.  Sample k of line l, channel c is at data[l * line_stride + k * elem_stride + c]
+// Two threads own one line of one channel (a column in the vertical pass, a row
+// in the horizontal pass) and run the two sweeps of the 4th-order recursion in
+// double exactly as gauss.c:175-196, one sweep each, exchanging their per-sample
+// state through a double scratch line; the sum of the two is narrowed to float.
+// Sample k of line l, channel c is at data[l * line_stride + k * elem_stride + c]
 // (floats).  In the vertical pass consecutive threads are consecutive
 // (column, channel) floats, so every step of the sweep is a coalesced row access.
 struct GaussCoeffs {
     double n_p[5], n_m[5], d_p[5], d_m[5], bd_p[5], bd_m[5];
 };
 
-// One recursion step.  s[0] is the current sample, s[1..4] the previous four in
-// sweep direction; v[1..4] the previous four outputs.  Order of operations as in
-// gauss.c:182-190: acc += n[i]*s[i] - d[i]*v[i] for i = 0..terms, then the
-// boundary terms (n[j] - bd[j]) * initial for j = terms+1..4.
-__device__ __forceinline__ double iir_step(const double *n, const double *d, const double *bd, double s0, double s1, double s2, double s3, double s4,
-                                           double v1, double v2, double v3, double v4, int terms, double initial) {
-    double acc = 0.0;
-    acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[0], s0), __dmul_rn(d[0], acc)));
-    if (terms >= 4) {  // steady state: no boundary terms
-        acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[1], s1), __dmul_rn(d[1], v1)));
-        acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[2], s2), __dmul_rn(d[2], v2)));
-        acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[3], s3), __dmul_rn(d[3], v3)));
-        acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[4], s4), __dmul_rn(d[4], v4)));
-        return acc;
-    }
-    if (terms >= 1) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[1], s1), __dmul_rn(d[1], v1)));
-    if (terms >= 2) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[2], s2), __dmul_rn(d[2], v2)));
-    if (terms >= 3) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(n[3], s3), __dmul_rn(d[3], v3)));
-    for (int j = terms + 1; j <= 4; ++j) acc = __dadd_rn(acc, __dmul_rn(__dsub_rn(n[j], bd[j]), initial));
+// The coefficients of one sweep direction, held in registers.
+struct IirCoeffs {
+    double n[5], d[5], nb[5];  // nb[j] = n[j] - bd[j], the factor of `initial` in the boundary terms
+};
+struct IirState {
+    double s1, s2, s3, s4, v1, v2, v3, v4;  // previous four samples and outputs in sweep direction
+};
+
+// One recursion step in the steady state (step index >= 4).  Order of operations
+// as in gauss.c:182-190: acc = 0; acc += n[i]*s[i] - d[i]*v[i] for i = 0..4, where
+// the i = 0 term reads acc itself for v[0] (still 0).  d[0] is 0.0 in both
+// directions, so "n[0]*s0 - d[0]*0.0" is n[0]*s0 bit for bit (x - 0 == x, also for
+// x == -0); the leading "0.0 +" stays because it turns -0 into +0.
+__device__ __forceinline__ double iir_step_steady(const IirCoeffs &c, double s0, const IirState &st) {
+    double acc = __dadd_rn(0.0, __dmul_rn(c.n[0], s0));
+    acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(c.n[1], st.s1), __dmul_rn(c.d[1], st.v1)));
+    acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(c.n[2], st.s2), __dmul_rn(c.d[2], st.v2)));
+    acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(c.n[3], st.s3), __dmul_rn(c.d[3], st.v3)));
+    acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(c.n[4], st.s4), __dmul_rn(c.d[4], st.v4)));
     return acc;
 }
 
-// Tiles of IIR_T steps: the samples (and, in the causal sweep, the anticausal
-// states) of the NEXT tile are loaded into registers before the current tile's
+// One of the first four steps of a sweep (terms = step index < 4): the recursion
+// terms that exist, then the boundary terms (n[j] - bd[j]) * initial for j = terms+1..4.
+__device__ __forceinline__ double iir_step_boundary(const IirCoeffs &c, double s0, const IirState &st, int terms, double initial) {
+    double acc = __dadd_rn(0.0, __dmul_rn(c.n[0], s0));
+    if (terms >= 1) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(c.n[1], st.s1), __dmul_rn(c.d[1], st.v1)));
+    if (terms >= 2) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(c.n[2], st.s2), __dmul_rn(c.d[2], st.v2)));
+    if (terms >= 3) acc = __dadd_rn(acc, __dsub_rn(__dmul_rn(c.n[3], st.s3), __dmul_rn(c.d[3], st.v3)));
+    if (terms < 1) acc = __dadd_rn(acc, __dmul_rn(c.nb[1], initial));
+    if (terms < 2) acc = __dadd_rn(acc, __dmul_rn(c.nb[2], initial));
+    if (terms < 3) acc = __dadd_rn(acc, __dmul_rn(c.nb[3], initial));
+    acc = __dadd_rn(acc, __dmul_rn(c.nb[4], initial));
+    return acc;
+}
+
+__device__ __forceinline__ void iir_shift(IirState &st, double s0, double acc) {
+    st.s4 = st.s3; st.s3 = st.s2; st.s2 = st.s1; st.s1 = s0;
+    st.v4 = st.v3; st.v3 = st.v2; st.v2 = st.v1; st.v1 = acc;
+}
+
+// Both sweeps of a line run CONCURRENTLY, one thread each, and meet in the
+// middle.  Neither sweep depends on the other's state, only the final sum does,
+// so (with h = ceil(n/2)):
+//   phase 1  causal thread:      k = 0 .. h-1,     stores its state vp[k] in the scratch line
+//            anticausal thread:  k = n-1 .. h,     stores its state vm[k]
+//   phase 2  causal thread:      k = h .. n-1,     out[k] = (float)(vp[k] + vm[k]) with vm[k] from the scratch line
+//            anticausal thread:  k = h-1 .. 0,     out[k] = (float)(vm[k] + vp[k]) with vp[k] from the scratch line
+// Every value is computed by the same double operations in the same order as
+// the sequential reference; only WHEN each output is written changes.  Compared
+// with one thread running both sweeps back to back this doubles the number of
+// independent recursions in flight and halves the length of each, at the same
+// memory traffic.  The pass may run in place: in phase 2 each thread reads
+// samples only from the half it then overwrites, and the four-sample history
+// that reaches across the middle is carried in registers.
+//
+// Tiles of IIR_T steps: the samples (and, in phase 2, the other sweep's states)
+// of the NEXT tile are loaded into registers before the current tile's
 // dependent chain of double operations runs, so global-memory latency overlaps
 // the recursion instead of stalling every step.
 #define IIR_T 8
-__global__ void __launch_bounds__(128) gauss_iir_lines_kernel(const float *in, float *out, double *scratch, int nlines, int n, long long line_stride,
-                                                              long long elem_stride, long long scratch_line_stride, long long scratch_elem_stride,
-                                                              GaussCoeffs C) {
-    int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= nlines * 4) return;
-    int line = tid >> 2, ch = tid & 3;
-    const float *p = in + (size_t)line * line_stride + ch;
-    float *o = out + (size_t)line * line_stride + ch;
-    double *sc = scratch + (size_t)line * scratch_line_stride + ch;
-    const int ntiles = (n + IIR_T - 1) / IIR_T;
 
-    // anticausal: k = n-1 .. 0 (step = n-1-k), uses samples and state to the right
-    {
-        const double initial = (double)p[(size_t)(n - 1) * elem_stride];
-        double s1 = 0, s2 = 0, s3 = 0, s4 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
-        float cur[IIR_T], nxt[IIR_T];
-#pragma unroll
-        for (int i = 0; i < IIR_T; ++i) { int k = n - 1 - i; nxt[i] = k >= 0 ? p[(size_t)k * elem_stride] : 0.f; }
-        for (int tile = 0; tile < ntiles; ++tile) {
-            const int step0 = tile * IIR_T;
-#pragma unroll
-            for (int i = 0; i < IIR_T; ++i) cur[i] = nxt[i];
-            if (tile + 1 < ntiles) {
-#pragma unroll
-                for (int i = 0; i < IIR_T; ++i) { int k = n - 1 - (step0 + IIR_T + i); nxt[i] = k >= 0 ? p[(size_t)k * elem_stride] : 0.f; }
-            }
-#pragma unroll
-            for (int i = 0; i < IIR_T; ++i) {
-                const int step = step0 + i, k = n - 1 - step;
-                if (k >= 0) {
-                    const double s0 = (double)cur[i];
-                    const double acc = iir_step(C.n_m, C.d_m, C.bd_m, s0, s1, s2, s3, s4, v1, v2, v3, v4, step < 4 ? step : 4, initial);
-                    sc[(size_t)k * scratch_elem_stride] = acc;
-                    s4 = s3; s3 = s2; s2 = s1; s1 = s0;
-                    v4 = v3; v3 = v2; v2 = v1; v1 = acc;
-                }
-            }
-        }
-    }
-    // causal: k = 0 .. n-1, then out = (float)(vp + vm)
-    {
-        const double initial = (double)p[0];
-        double s1 = 0, s2 = 0, s3 = 0, s4 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+// one step without prefetch: the boundary steps and the tail that does not fill a tile
+template <bool COMBINE>
+__device__ __forceinline__ void iir_single(IirState &st, const IirCoeffs &c, const float *pp, float *oo, double *ss, int t, double initial) {
+    const double s0 = (double)*pp;
+    const double acc = t < 4 ? iir_step_boundary(c, s0, st, t, initial) : iir_step_steady(c, s0, st);
+    if (COMBINE) *oo = (float)__dadd_rn(acc, *ss);
+    else *ss = acc;
+    iir_shift(st, s0, acc);
+}
+
+// steps t0 .. t1-1 of one sweep; pp/oo/ss point at the sample of step t0, de/ds
+// are the signed strides (floats / doubles) from one step to the next
+template <bool COMBINE>
+__device__ __forceinline__ void iir_run(IirState &st, const IirCoeffs &c, const float *pp, float *oo, double *ss, long long de, long long ds, int t0, int t1,
+                                        double initial) {
+    int t = t0;
+#pragma unroll 1
+    for (; t < t1 && t < 4; ++t, pp += de, oo += de, ss += ds) iir_single<COMBINE>(st, c, pp, oo, ss, t, initial);
+    const int ntiles = t1 > t ? (t1 - t) / IIR_T : 0;
+    if (ntiles > 0) {
         float cur[IIR_T], nxt[IIR_T];
         double curv[IIR_T], nxtv[IIR_T];
 #pragma unroll
         for (int i = 0; i < IIR_T; ++i) {
-            nxt[i] = i < n ? p[(size_t)i * elem_stride] : 0.f;
-            nxtv[i] = i < n ? sc[(size_t)i * scratch_elem_stride] : 0.0;
+            nxt[i] = pp[i * de];
+            if (COMBINE) nxtv[i] = ss[i * ds];
         }
+#pragma unroll 1
         for (int tile = 0; tile < ntiles; ++tile) {
-            const int k0 = tile * IIR_T;
 #pragma unroll
-            for (int i = 0; i < IIR_T; ++i) { cur[i] = nxt[i]; curv[i] = nxtv[i]; }
+            for (int i = 0; i < IIR_T; ++i) { cur[i] = nxt[i]; if (COMBINE) curv[i] = nxtv[i]; }
             if (tile + 1 < ntiles) {
 #pragma unroll
                 for (int i = 0; i < IIR_T; ++i) {
-                    int k = k0 + IIR_T + i;
-                    nxt[i] = k < n ? p[(size_t)k * elem_stride] : 0.f;
-                    nxtv[i] = k < n ? sc[(size_t)k * scratch_elem_stride] : 0.0;
+                    nxt[i] = pp[(IIR_T + i) * de];
+                    if (COMBINE) nxtv[i] = ss[(IIR_T + i) * ds];
                 }
             }
 #pragma unroll
             for (int i = 0; i < IIR_T; ++i) {
-                const int k = k0 + i;
-                if (k < n) {
-                    const double s0 = (double)cur[i];
-                    const double acc = iir_step(C.n_p, C.d_p, C.bd_p, s0, s1, s2, s3, s4, v1, v2, v3, v4, k < 4 ? k : 4, initial);
-                    o[(size_t)k * elem_stride] = (float)__dadd_rn(acc, curv[i]);
-                    s4 = s3; s3 = s2; s2 = s1; s1 = s0;
-                    v4 = v3; v3 = v2; v2 = v1; v1 = acc;
-                }
+                const double s0 = (double)cur[i];
+                const double acc = iir_step_steady(c, s0, st);
+                if (COMBINE) oo[i * de] = (float)__dadd_rn(acc, curv[i]);
+                else ss[i * ds] = acc;
+                iir_shift(st, s0, acc);
             }
+            pp += IIR_T * de; oo += IIR_T * de; ss += IIR_T * ds;
         }
+        t += ntiles * IIR_T;
     }
+#pragma unroll 1
+    for (; t < t1; ++t, pp += de, oo += de, ss += ds) iir_single<COMBINE>(st, c, pp, oo, ss, t, initial);
+}
+
+// Block = IIR_PAIRS causal threads followed by IIR_PAIRS anticausal threads for
+// the same IIR_PAIRS (line, channel) recursions; the sweep direction is uniform
+// per warp, the hand-over between the phases is one __syncthreads().
+#define IIR_PAIRS 32
+__global__ void __launch_bounds__(2 * IIR_PAIRS) gauss_iir_lines_kernel(const float *in, float *out, double *scratch, int nlines, int n, long long line_stride,
+                                                                         long long elem_stride, long long scratch_line_stride,
+                                                                         long long scratch_elem_stride, GaussCoeffs C) {
+    const int anti = threadIdx.x >= IIR_PAIRS;
+    const int pair = blockIdx.x * IIR_PAIRS + (threadIdx.x - (anti ? IIR_PAIRS : 0));
+    const bool valid = pair < nlines * 4;
+    const int line = valid ? pair >> 2 : 0, ch = pair & 3;
+    const int nn = valid ? n : 0;
+    const int h = nn - nn / 2;                      // causal phase 1 covers [0, h), anticausal [h, n)
+    const int len1 = anti ? nn - h : h;
+    const int k0 = anti ? nn - 1 : 0;
+    const long long de = anti ? -elem_stride : elem_stride, ds = anti ? -scratch_elem_stride : scratch_elem_stride;
+    const float *p = in + (size_t)line * line_stride + ch + (long long)k0 * elem_stride;
+    float *o = out + (size_t)line * line_stride + ch + (long long)k0 * elem_stride;
+    double *sc = scratch + (size_t)line * scratch_line_stride + ch + (long long)k0 * scratch_elem_stride;
+    IirCoeffs c;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        c.n[i] = anti ? C.n_m[i] : C.n_p[i];
+        c.d[i] = anti ? C.d_m[i] : C.d_p[i];
+        c.nb[i] = __dsub_rn(c.n[i], anti ? C.bd_m[i] : C.bd_p[i]);
+    }
+    IirState st = {0, 0, 0, 0, 0, 0, 0, 0};
+    double initial = 0.0;
+    if (nn > 0) initial = (double)*p;
+    iir_run<false>(st, c, p, o, sc, de, ds, 0, len1, initial);
+    __syncthreads();
+    iir_run<true>(st, c, p + len1 * de, o + len1 * de, sc + len1 * ds, de, ds, len1, nn, initial);
 }
 
 // gauss.c:39-115, evaluated on the host in double exactly like the reference
@@ -206,13 +252,13 @@ void launch_gauss_iir(const float *in, float *out, double *scratch, int width, i
     find_iir_constants(c, sigma_v);
     {
         int threads = width * 4;
-        gauss_iir_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(in, out, scratch, width, height, 4, (long long)width * 4, 4, (long long)width * 4, c);
+        gauss_iir_lines_kernel<<<(threads + IIR_PAIRS - 1) / IIR_PAIRS, 2 * IIR_PAIRS, 0, stream>>>(in, out, scratch, width, height, 4, (long long)width * 4, 4, (long long)width * 4, c);
     }
     // horizontal pass: lines are rows, in place on `out`
     find_iir_constants(c, sigma_h);
     {
         int threads = height * 4;
-        gauss_iir_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(out, out, scratch, height, width, (long long)width * 4, 4, (long long)width * 4, 4, c);
+        gauss_iir_lines_kernel<<<(threads + IIR_PAIRS - 1) / IIR_PAIRS, 2 * IIR_PAIRS, 0, stream>>>(out, out, scratch, height, width, (long long)width * 4, 4, (long long)width * 4, 4, c);
     }
 }
 

@@ -290,3 +290,17 @@ mmo_image *native_filter_gaussian_blur(mmo_invocation *invocation, mmo_userval *
     invocation->cache = e;
     return result;
 }
+
+/* Float-level entry for the tests: blurs data[height][width][4] in place with pixel-unit sigmas, the same dispatch
+ * (IIR for sigma >= 0.5 px on both axes, truncated FIR otherwise) as native_filter_gaussian_blur above. */
+void mmo_gaussian_blur_floats(float *data, int width, int height, float sigma_h_px, float sigma_v_px) {
+    mmo_pools pools;
+    mmo_image *fm, *result;
+    mmo_pools_init(&pools);
+    fm = mmo_floatmap_alloc(width, height, &pools);
+    memcpy(fm->fdata, data, sizeof(float) * 4 * (size_t)width * height);
+    if (sigma_h_px < 0.5 || sigma_v_px < 0.5) result = gauss_rle(fm, sigma_h_px, sigma_v_px, &pools);
+    else result = gauss_iir(fm, sigma_h_px, sigma_v_px, &pools);
+    memcpy(data, result->fdata, sizeof(float) * 4 * (size_t)width * height);
+    mmo_pools_free(&pools);
+}

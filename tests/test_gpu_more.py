@@ -217,3 +217,31 @@ def test_fft_native_filters_match_oracle(size):
         got, want = run_both(src, w, h, uv)
         exact, le1, mx = compare_u8(got, want)
         assert le1 >= 99.9 and exact >= 99.0, (src.split()[1], size, exact, le1, mx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,sh,sv", [(383, 257, 6.5, 3.25), (64, 48, 0.75, 12.0), (5, 3, 1.0, 1.0), (1, 1, 2.0, 2.0), (2, 7, 0.5, 0.5),
+                                       (9, 1, 3.0, 3.0), (130, 17, 0.3, 0.4), (31, 33, 0.45, 2.0)])
+def test_gaussian_blur_device_bit_exact_floats(w, h, sh, sv):
+    """mmb_gaussian_blur_device on float data against the oracle's gauss.c restatement, compared as raw float bits.
+    Odd, tiny and one-sample lines exercise the meet-in-the-middle hand-over of the two concurrent IIR sweeps."""
+    import ctypes
+    import torch
+    rng = np.random.default_rng(w * 1000 + h)
+    data = rng.random((h, w, 4), dtype=np.float32)
+    data[rng.random((h, w)) < 0.3] = 0.0  # runs of equal samples: the FIR's run-length variant
+    want = np.ascontiguousarray(data.copy())
+    olib = OracleFilter(mb.Module(source="filter f () rgba:[1,0,0,1] end").ir).lib
+    olib.mmo_gaussian_blur_floats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]
+    olib.mmo_gaussian_blur_floats.restype = None
+    olib.mmo_gaussian_blur_floats(want.ctypes.data, w, h, sh, sv)
+    src = torch.from_numpy(data).cuda()
+    dst = torch.empty_like(src)
+    rc = mb.lib().mmb_gaussian_blur_device(0, src.data_ptr(), dst.data_ptr(), w, h, sh, sv, None)
+    assert rc == 0, mb._err()
+    got = dst.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "max abs diff %g" % np.abs(got - want).max()
+    # in place (the horizontal pass always is; here the whole call)
+    rc = mb.lib().mmb_gaussian_blur_device(0, src.data_ptr(), src.data_ptr(), w, h, sh, sv, None)
+    assert rc == 0, mb._err()
+    assert np.array_equal(src.cpu().numpy().view(np.uint32), want.view(np.uint32))
