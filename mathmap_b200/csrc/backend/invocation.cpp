@@ -108,6 +108,8 @@ struct mmb_invocation {
     size_t staging2_bytes = 0;
     void *default_curve = nullptr, *default_gradient = nullptr;
     cudaStream_t copy_stream = nullptr;  // device->host copies overlap the next chunk's kernel
+    cudaStream_t aux_stream = nullptr;   // odd chunks render here so one chunk's tail overlaps the next chunk's head
+    cudaEvent_t order_event = nullptr;
     std::vector<cudaEvent_t> chunk_events;
 
     void *alloc(size_t bytes) {
@@ -757,6 +759,8 @@ void mmb_invocation_free(mmb_invocation *inv) {
         if (u.table) cudaFree(u.table);
     for (auto &c : inv->coord_cache) cudaFree(c.second);
     for (auto e : inv->chunk_events) cudaEventDestroy(e);
+    if (inv->aux_stream) cudaStreamDestroy(inv->aux_stream);
+    if (inv->order_event) cudaEventDestroy(inv->order_event);
     if (inv->copy_stream) cudaStreamDestroy(inv->copy_stream);
     if (inv->staging) cudaFree(inv->staging);
     if (inv->staging2) cudaFree(inv->staging2);
@@ -964,28 +968,46 @@ int mmb_calc_lines(mmb_invocation *inv, int first_row, int last_row, void *q, in
         size_t row_bytes = floatmap ? sizeof(float) * 4 * (size_t)inv->W : (size_t)inv->W * inv->bpp;
         size_t bytes = row_bytes * (size_t)(lr - fr);
         void *d = inv->ensure_staging(inv->staging, inv->staging_bytes, bytes);
-        // The band is rendered in chunks; the device->host copy of chunk i runs on a second stream while
-        // the kernel of chunk i+1 runs (q pinned: true overlap; pageable q: still correct).
+        // The band is rendered in chunks; the device->host copy of chunk i runs on a copy stream while the
+        // kernels of the following chunks run (q pinned: true overlap; pageable q: still correct).  Chunks
+        // alternate between two compute streams, so the last blocks of one chunk (rows of a filter differ in
+        // cost) do not leave the device idle before the next chunk starts.
         int rows = lr - fr;
         int chunks = 1;
-        if (!inv->cfg.supersampling && bytes >= ((size_t)8 << 20)) chunks = (int)std::min<size_t>(16, std::max<size_t>(2, bytes >> 25));
+        if (!inv->cfg.supersampling && bytes >= ((size_t)8 << 20)) chunks = (int)std::min<size_t>(32, std::max<size_t>(2, bytes >> 25));
         int chunk_rows = ((rows + chunks - 1) / chunks + 7) & ~7;
         if (!inv->copy_stream) ck(cudaStreamCreateWithFlags(&inv->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        int ci = 0;
-        for (int r0 = fr; r0 < lr; r0 += chunk_rows, ++ci) {
-            int r1 = std::min(lr, r0 + chunk_rows);
-            char *dchunk = (char *)d + (size_t)(r0 - fr) * row_bytes;
-            render_band(inv, r0, r1, dchunk, floatmap);
-            if ((int)inv->chunk_events.size() <= ci) {
-                cudaEvent_t e;
-                ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
-                inv->chunk_events.push_back(e);
-            }
-            ck(cudaEventRecord(inv->chunk_events[ci], inv->stream), "cudaEventRecord");
-            ck(cudaStreamWaitEvent(inv->copy_stream, inv->chunk_events[ci], 0), "cudaStreamWaitEvent");
-            ck(cudaMemcpyAsync((char *)q + (size_t)(r0 - fr) * row_bytes, dchunk, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, inv->copy_stream),
-               "cudaMemcpyAsync(D2H)");
+        if (!inv->aux_stream) ck(cudaStreamCreateWithFlags(&inv->aux_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!inv->order_event) ck(cudaEventCreateWithFlags(&inv->order_event, cudaEventDisableTiming), "cudaEventCreate");
+        cudaStream_t main_stream = inv->stream;
+        if (chunks > 1) {  // everything queued so far (init_frame's renders and blurs) precedes the chunks on both streams
+            ck(cudaEventRecord(inv->order_event, main_stream), "cudaEventRecord");
+            ck(cudaStreamWaitEvent(inv->aux_stream, inv->order_event, 0), "cudaStreamWaitEvent");
         }
+        int ci = 0;
+        try {
+            for (int r0 = fr; r0 < lr; r0 += chunk_rows, ++ci) {
+                int r1 = std::min(lr, r0 + chunk_rows);
+                char *dchunk = (char *)d + (size_t)(r0 - fr) * row_bytes;
+                inv->stream = (ci & 1) ? inv->aux_stream : main_stream;
+                render_band(inv, r0, r1, dchunk, floatmap);
+                if ((int)inv->chunk_events.size() <= ci) {
+                    cudaEvent_t e;
+                    ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+                    inv->chunk_events.push_back(e);
+                }
+                ck(cudaEventRecord(inv->chunk_events[ci], inv->stream), "cudaEventRecord");
+                ck(cudaStreamWaitEvent(inv->copy_stream, inv->chunk_events[ci], 0), "cudaStreamWaitEvent");
+                ck(cudaMemcpyAsync((char *)q + (size_t)(r0 - fr) * row_bytes, dchunk, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDeviceToHost,
+                                   inv->copy_stream),
+                   "cudaMemcpyAsync(D2H)");
+            }
+        } catch (...) {
+            inv->stream = main_stream;
+            throw;
+        }
+        inv->stream = main_stream;
+        ck(cudaStreamSynchronize(inv->aux_stream), "cudaStreamSynchronize");
         ck(cudaStreamSynchronize(inv->copy_stream), "cudaStreamSynchronize");
         ck(cudaStreamSynchronize(inv->stream), "cudaStreamSynchronize");
     });
