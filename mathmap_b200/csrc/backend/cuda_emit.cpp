@@ -1,4 +1,5 @@
 #include "cuda_emit.h"
+#include "../runtime/mm_types.h"
 
 #include <cmath>
 #include <cstring>
@@ -93,6 +94,7 @@ struct Emitter {
     std::vector<const Value *> row_exports;  // level-1 values the pixel kernel reads
     std::set<const Filter *> &called;  // filters reached through RHS_FILTER
     std::set<const Stmt *> fused;       // statements already emitted as part of a fused pair
+    std::string slot_prefix;            // kernels: image uniforms are referenced as the enum constant <slot_prefix><value>
 
     Emitter(const mmb_module &m, const FilterCode &c, Mode md, std::set<const Filter *> &cl) : mod(m), code(c), mode(md), call_flavour(md == CALL), called(cl) {}
 
@@ -136,6 +138,7 @@ struct Emitter {
         if (!on_device(v->level)) {
             if (v->level == 0) {
                 if (uniform_set_p->insert(v).second) uniform_order_p->push_back(v);
+                if (v->cv->type == T_IMAGE && !slot_prefix.empty()) return slot_prefix + vname(v);
                 return "U." + vname(v);
             }
             if (mode == PIXEL_ONLY && v->level == 1) {  // loaded from the row arrays at kernel entry
@@ -468,12 +471,14 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         }
         const bool use_rows = row_cost >= 20;
         Emitter e(m, *code, use_rows ? Emitter::PIXEL_ONLY : Emitter::PIXEL_ALL, called);
+        e.slot_prefix = "mm_slot_" + name + "_";
         // body first (discovers uniforms and row exports)
         std::vector<const Value *> decls;
         e.collect_decls(code->first, decls);
         e.emit_stmts(code->first, "    ");
         std::string body = e.out.str();
         Emitter er(m, *code, Emitter::ROW, called);
+        er.slot_prefix = e.slot_prefix;
         er.uniform_set_p = &e.own_uniform_set;
         er.uniform_order_p = &e.own_uniform_order;
         std::vector<const Value *> row_decls;
@@ -494,7 +499,8 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
             return big(a) && !big(b);
         });
         size_t off = 0;
-        std::ostringstream st;
+        int image_slots = 0;
+        std::ostringstream st, slots;
         st << "struct mm_uniforms_" << name << " {\n";
         for (const Value *v : order) {
             UniformField uf;
@@ -504,12 +510,17 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
             uf.size = field_size(uf.type, uf.tuple_len);
             uf.offset = off;
             off += uf.size;
+            if (uf.type == T_IMAGE) {
+                if (image_slots >= MM_MAX_IMAGES) unsupported("more than " + std::to_string(MM_MAX_IMAGES) + " image values in one filter");
+                uf.image_slot = image_slots++;
+                slots << "enum { " << e.slot_prefix << Emitter::vname(v) << " = " << uf.image_slot << " };\n";
+            }
             k.uniforms.push_back(uf);
             st << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
         }
         if (off == 0) { st << "    int mm_unused;\n"; off = 4; }
         off = (off + 7) & ~(size_t)7;
-        st << "};\n";
+        st << "};\n" << slots.str();
         k.uniforms_size = off;
 
         // row arrays: one 4-byte array per scalar component of every exported row-constant value

@@ -18,6 +18,7 @@ struct UniformField {
     int tuple_len;
     size_t offset;
     size_t size;
+    int image_slot = -1;  // T_IMAGE: index into mm_params::images, fixed at compile time
 };
 
 struct FilterKernel {

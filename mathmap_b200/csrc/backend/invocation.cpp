@@ -176,6 +176,12 @@ mm_image to_device_desc(const HostImage &h) {
     d.sx = h.sx; d.sy = h.sy; d.mx = h.mx; d.my = h.my;
     d.ax = h.ax; d.bx = h.bx; d.ay = h.ay; d.by = h.by;
     d.xf = h.xf; d.yf = h.yf;
+    const bool fast = d.kind == MM_IMAGE_DRAWABLE && h.w > 0 && h.h > 0 && h.w < (1 << 22) && h.h < (1 << 22);
+    d.fast_w = fast ? (float)h.w : -1.0f;
+    d.fast_h = fast ? (float)h.h : -1.0f;
+    d.fast_wm1 = fast ? (float)(h.w - 1) : -1.0f;
+    d.fast_hm1 = fast ? (float)(h.h - 1) : -1.0f;
+    d.fast_nf = fast ? (float)h.num_frames : -1.0f;
     return d;
 }
 
@@ -401,7 +407,7 @@ struct Replay {
 void pack_frame(mmb_invocation *inv, const FilterKernel &k, Replay &rp, FrameData &fd) {
     fd.uniforms.assign(k.uniforms_size, 0);
     fd.nslots = 0;
-    std::map<int, int> slot_of;
+    memset(fd.slots, 0, sizeof fd.slots);
     for (const UniformField &u : k.uniforms) {
         auto it = rp.env.find(u.value);
         // a frame-constant value defined in the branch of a frame-constant `if` the host did not take
@@ -416,18 +422,15 @@ void pack_frame(mmb_invocation *inv, const FilterKernel &k, Replay &rp, FrameDat
         case T_COLOR: memcpy(dst, &v.color, 4); break;
         case T_CURVE: case T_GRADIENT: memcpy(dst, &v.ptr, 8); break;
         case T_IMAGE: {
-            int slot;
-            auto s = slot_of.find(v.image);
-            if (s != slot_of.end()) slot = s->second;
-            else {
-                if (v.image < 0 || v.image >= (int)inv->images.size()) fail("internal error: bad image handle");
-                const HostImage &img = inv->images[v.image];
-                if (img.kind == IMG_CLOSURE) fail("a closure image reaches per-pixel code without being called directly; this is not supported");
-                if (fd.nslots >= MM_MAX_IMAGES) fail("too many distinct images in one filter (max 16)");
-                slot = fd.nslots++;
-                fd.slots[slot] = to_device_desc(img);
-                slot_of[v.image] = slot;
-            }
+            // every image-typed uniform owns the slot the kernel was compiled with (cuda_emit.cpp), so the
+            // generated code indexes P.images with a literal
+            if (v.image < 0 || v.image >= (int)inv->images.size()) fail("internal error: bad image handle");
+            const HostImage &img = inv->images[v.image];
+            if (img.kind == IMG_CLOSURE) fail("a closure image reaches per-pixel code without being called directly; this is not supported");
+            int slot = u.image_slot;
+            if (slot < 0 || slot >= MM_MAX_IMAGES) fail("internal error: image slot out of range");
+            fd.slots[slot] = to_device_desc(img);
+            fd.nslots = std::max(fd.nslots, slot + 1);
             memcpy(dst, &slot, 4);
             break;
         }

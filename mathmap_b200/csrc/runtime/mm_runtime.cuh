@@ -409,14 +409,13 @@ MM_DEV float mm_floor_small_nonneg(float v) {
     return r > v ? __fsub_rn(r, 1.0f) : r;
 }
 
-MM_DEV bool mm_bilinear_interior(const mm_params &P, const mm_image &img, float x, float y, int frame, mm_tup<4> &out) {
+MM_DEV bool mm_bilinear_interior(const mm_params &P, const mm_image &img, float x, float y, float t, mm_tup<4> &out) {
 #if MM_EDGE_X == 0 && MM_EDGE_Y == 0
     const float px = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
     const float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
-    // x1 = floor(px) in [0, w-2] and y1 in [0, h-2]  <=>  0 <= px < w-1 and 0 <= py < h-1 (w, h < 2^22)
-    const float wm1 = (float)(img.w - 1), hm1 = (float)(img.h - 1);
-    if (!(px >= 0.0f && px < wm1 && py >= 0.0f && py < hm1 && img.w < (1 << 22) && img.h < (1 << 22) && (unsigned)frame < (unsigned)img.num_frames))
-        return false;
+    // x1 = floor(px) in [0, w-2] and y1 in [0, h-2]  <=>  0 <= px < w-1 and 0 <= py < h-1 (w, h < 2^22: the host
+    // sets the fast_* bounds to -1 otherwise).  The frame (int)t, truncated, is valid  <=>  -1 < t < num_frames.
+    if (!(px >= 0.0f && px < img.fast_wm1 && py >= 0.0f && py < img.fast_hm1 && t > -1.0f && t < img.fast_nf)) return false;
     const float fx = mm_floor_small_nonneg(px), fy = mm_floor_small_nonneg(py);
     const unsigned x1 = (unsigned)__float_as_int(__fadd_rn(fx, 8388608.0f)) & 0x7fffffu;
     const unsigned y1 = (unsigned)__float_as_int(__fadd_rn(fy, 8388608.0f)) & 0x7fffffu;
@@ -440,7 +439,7 @@ MM_DEV bool mm_bilinear_interior(const mm_params &P, const mm_image &img, float 
 #endif
 }
 
-MM_DEV bool mm_nearest_interior(const mm_params &P, const mm_image &img, float x, float y, int frame, mm_tup<4> &out) {
+MM_DEV bool mm_nearest_interior(const mm_params &P, const mm_image &img, float x, float y, float t, mm_tup<4> &out) {
 #if MM_EDGE_X == 0 && MM_EDGE_Y == 0
     float px = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
     float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
@@ -448,13 +447,12 @@ MM_DEV bool mm_nearest_interior(const mm_params &P, const mm_image &img, float x
     px = __fadd_rn(px, 0.5f);
     py = __fadd_rn(py, 0.5f);
 #endif
-    if (!(px >= 0.0f && px < (float)img.w && py >= 0.0f && py < (float)img.h && img.w < (1 << 22) && img.h < (1 << 22) && (unsigned)frame < (unsigned)img.num_frames))
-        return false;
+    if (!(px >= 0.0f && px < img.fast_w && py >= 0.0f && py < img.fast_h && t > -1.0f && t < img.fast_nf)) return false;
     const unsigned x1 = (unsigned)__float_as_int(__fadd_rn(mm_floor_small_nonneg(px), 8388608.0f)) & 0x7fffffu;
     const unsigned y1 = (unsigned)__float_as_int(__fadd_rn(mm_floor_small_nonneg(py), 8388608.0f)) & 0x7fffffu;
-    const unsigned t = __ldg((const unsigned *)img.data + (y1 * (unsigned)img.w + x1));
+    const unsigned texel = __ldg((const unsigned *)img.data + (y1 * (unsigned)img.w + x1));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out.v[k] = mm_unit_from_rounded(mm_byte_as_float(t, 0x7650u | (unsigned)k));
+    for (int k = 0; k < 4; ++k) out.v[k] = mm_unit_from_rounded(mm_byte_as_float(texel, 0x7650u | (unsigned)k));
     return true;
 #else
     return false;
@@ -478,14 +476,13 @@ MM_DEV mm_tup<4> mm_orig_val(const mm_params &P, int image, float x, float y, fl
     x = __fmul_rn(x, img.xf);  // 1.0 unless a RESIZE wrapper survived to run time
     y = __fmul_rn(y, img.yf);
     if (img.kind == MM_IMAGE_FLOATMAP) return mm_floatmap_pixel(img, x, y);
-    int frame = mm_f2i(t);
     mm_tup<4> r;
 #if MM_AA
-    if (mm_bilinear_interior(P, img, x, y, frame, r)) return r;
-    return mm_tuple_from_color(mm_sample_bilinear(P, img, x, y, frame));
+    if (mm_bilinear_interior(P, img, x, y, t, r)) return r;
+    return mm_tuple_from_color(mm_sample_bilinear(P, img, x, y, mm_f2i(t)));
 #else
-    if (mm_nearest_interior(P, img, x, y, frame, r)) return r;
-    return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, frame));
+    if (mm_nearest_interior(P, img, x, y, t, r)) return r;
+    return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, mm_f2i(t)));
 #endif
 }
 // the nearest sampler regardless of MM_AA: render_image of a drawable (builtins.c:306)

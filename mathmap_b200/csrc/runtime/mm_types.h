@@ -1,7 +1,7 @@
 // Plain structs shared by host code and device code (NVRTC and nvcc).
 #pragma once
 
-#define MM_MAX_IMAGES 16
+#define MM_MAX_IMAGES 24
 #define MM_CURVE_POINTS 1024
 
 typedef unsigned int mm_color;
@@ -18,7 +18,10 @@ struct mm_image {
     float sx, sy, mx, my;  // drawable: scale and middle (userval.c:263-279)
     float ax, bx, ay, by;  // floatmap: pixel = a * coord + b
     float xf, yf;          // resize factors applied to sampling coordinates (opmacros.h:203-207)
-    int pad0, pad1;
+    // Bounds of the samplers' interior fast paths as floats, filled by the host: w, h, w-1, h-1 and num_frames
+    // when w, h < 2^22 and the image is a drawable, else all -1 (the fast-path tests then never hold).
+    float fast_w, fast_h, fast_wm1, fast_hm1, fast_nf;
+    int pad0;
 };
 
 // Per-launch parameters (the invocation / frame / slice fields calc_lines reads,
