@@ -281,6 +281,17 @@ struct Emitter {
         case OP_USERVAL_INT: case OP_USERVAL_FLOAT: case OP_USERVAL_BOOL: case OP_USERVAL_COLOR:
         case OP_USERVAL_CURVE: case OP_USERVAL_GRADIENT: case OP_USERVAL_IMAGE:
             return userval_access(op->id, r->args[0]);
+        case OP_ELL_INT_K_COMP: return fn1("mm_ell_int_k_comp");
+        case OP_ELL_INT_E_COMP: return fn1("mm_ell_int_e_comp");
+        case OP_ELL_INT_F: return fn2("mm_ell_int_f");
+        case OP_ELL_INT_E: return fn2("mm_ell_int_e");
+        case OP_ELL_INT_P: return "mm_ell_int_p(" + F(0) + ", " + F(1) + ", " + F(2) + ")";
+        case OP_ELL_INT_D: return "mm_ell_int_d(" + F(0) + ", " + F(1) + ")";  // the third argument is unused by GSL
+        case OP_ELL_INT_RC: return fn2("mm_ell_int_rc");
+        case OP_ELL_INT_RD: return "mm_ell_int_rd(" + F(0) + ", " + F(1) + ", " + F(2) + ")";
+        case OP_ELL_INT_RF: return "mm_ell_int_rf(" + F(0) + ", " + F(1) + ", " + F(2) + ")";
+        case OP_ELL_INT_RJ: return "mm_ell_int_rj(" + F(0) + ", " + F(1) + ", " + F(2) + ", " + F(3) + ")";
+        case OP_ELL_JAC: return fn2("mm_ell_jac");
         case OP_RAND: return "mm_rand(mm_rng, " + F(0) + ", " + F(1) + ")";
         case OP_SOLVE_LINEAR_2: return "mm_solve_linear_2(" + A(0) + ", " + A(1) + ")";
         case OP_SOLVE_LINEAR_3: return "mm_solve_linear_3(" + A(0) + ", " + A(1) + ")";

@@ -2,6 +2,7 @@
 // frame-constant IR (the reference's init_frame, new_template.c.in:314-337),
 // render_image / native filters as kernel launches, and calc_lines as one
 // pixel-grid launch per band (new_template.c.in:208-312).
+#include "../runtime/mm_elliptic.h"
 #include <cuda_runtime_api.h>
 
 #include <cmath>
@@ -334,6 +335,13 @@ struct Replay {
         case OP_GREEN: v.type = T_FLOAT; v.f = (float)(((a[0].color >> 16) & 0xff) / 255.0); return v;
         case OP_BLUE: v.type = T_FLOAT; v.f = (float)(((a[0].color >> 8) & 0xff) / 255.0); return v;
         case OP_ALPHA: v.type = T_FLOAT; v.f = (float)((a[0].color & 0xff) / 255.0); return v;
+        case OP_ELL_JAC: {  // opmacros.h:119-125
+            double sn, cn, dn;
+            mm_elljac((double)as_float(a[0]), (double)as_float(a[1]), &sn, &cn, &dn);
+            v.type = T_TUPLE;
+            v.tuple = {(float)sn, (float)cn, (float)dn};
+            return v;
+        }
         case OP_TUPLE_NTH: {
             int n = a[1].i;
             v.type = T_FLOAT;

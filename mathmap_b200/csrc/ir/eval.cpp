@@ -6,6 +6,7 @@
 // argument type, call the C expression (libm in double on float arguments) and
 // narrow to the op's result type; TP_MAX / TP_MAX_FLOAT ops first cast all
 // arguments to the widest argument type.
+#include "../runtime/mm_elliptic.h"
 #include <cmath>
 #include <complex>
 
@@ -147,6 +148,17 @@ bool eval_op(const OpInfo *op, const Const *a, Const *out) {
     case OP_C_ASINH: *out = mk_c(from_c(__builtin_casinhf(Z(0)))); return true;
     case OP_C_ACOSH: *out = mk_c(from_c(__builtin_cacoshf(Z(0)))); return true;
     case OP_C_ATANH: *out = mk_c(from_c(__builtin_catanhf(Z(0)))); return true;
+    // GSL elliptic integrals (opmacros.h:101-117), restated in ../runtime/mm_elliptic.h
+    case OP_ELL_INT_K_COMP: *out = mk_f((float)mm_ellint_kcomp(D(0))); return true;
+    case OP_ELL_INT_E_COMP: *out = mk_f((float)mm_ellint_ecomp(D(0))); return true;
+    case OP_ELL_INT_F: *out = mk_f((float)mm_ellint_f(D(0), D(1))); return true;
+    case OP_ELL_INT_E: *out = mk_f((float)mm_ellint_e(D(0), D(1))); return true;
+    case OP_ELL_INT_P: *out = mk_f((float)mm_ellint_p(D(0), D(1), D(2))); return true;
+    case OP_ELL_INT_D: *out = mk_f((float)mm_ellint_d(D(0), D(1))); return true;
+    case OP_ELL_INT_RC: *out = mk_f((float)mm_ellint_rc(D(0), D(1))); return true;
+    case OP_ELL_INT_RD: *out = mk_f((float)mm_ellint_rd(D(0), D(1), D(2))); return true;
+    case OP_ELL_INT_RF: *out = mk_f((float)mm_ellint_rf(D(0), D(1), D(2))); return true;
+    case OP_ELL_INT_RJ: *out = mk_f((float)mm_ellint_rj(D(0), D(1), D(2), D(3))); return true;
     default: return false;
     }
 }

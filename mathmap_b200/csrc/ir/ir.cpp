@@ -115,16 +115,16 @@ static OpInfo k_ops[NUM_OPS] = {
     {OP_C_ACOSH, "cacoshf", 1, TP_CONST, C, true, true, {C}},
     {OP_C_ATANH, "catanhf", 1, TP_CONST, C, true, true, {C}},
     {OP_C_GAMMA, "cgamma", 1, TP_CONST, C, true, false, {C}},
-    {OP_ELL_INT_K_COMP, "ELL_INT_K_COMP", 1, TP_CONST, F, true, false, {F}},
-    {OP_ELL_INT_E_COMP, "ELL_INT_E_COMP", 1, TP_CONST, F, true, false, {F}},
-    {OP_ELL_INT_F, "ELL_INT_F", 2, TP_CONST, F, true, false, {F, F}},
-    {OP_ELL_INT_E, "ELL_INT_E", 2, TP_CONST, F, true, false, {F, F}},
-    {OP_ELL_INT_P, "ELL_INT_P", 3, TP_CONST, F, true, false, {F, F, F}},
-    {OP_ELL_INT_D, "ELL_INT_D", 3, TP_CONST, F, true, false, {F, F, F}},
-    {OP_ELL_INT_RC, "ELL_INT_RC", 2, TP_CONST, F, true, false, {F, F}},
-    {OP_ELL_INT_RD, "ELL_INT_RD", 3, TP_CONST, F, true, false, {F, F, F}},
-    {OP_ELL_INT_RF, "ELL_INT_RF", 3, TP_CONST, F, true, false, {F, F, F}},
-    {OP_ELL_INT_RJ, "ELL_INT_RJ", 4, TP_CONST, F, true, false, {F, F, F, F}},
+    {OP_ELL_INT_K_COMP, "ELL_INT_K_COMP", 1, TP_CONST, F, true, true, {F}},
+    {OP_ELL_INT_E_COMP, "ELL_INT_E_COMP", 1, TP_CONST, F, true, true, {F}},
+    {OP_ELL_INT_F, "ELL_INT_F", 2, TP_CONST, F, true, true, {F, F}},
+    {OP_ELL_INT_E, "ELL_INT_E", 2, TP_CONST, F, true, true, {F, F}},
+    {OP_ELL_INT_P, "ELL_INT_P", 3, TP_CONST, F, true, true, {F, F, F}},
+    {OP_ELL_INT_D, "ELL_INT_D", 3, TP_CONST, F, true, true, {F, F, F}},
+    {OP_ELL_INT_RC, "ELL_INT_RC", 2, TP_CONST, F, true, true, {F, F}},
+    {OP_ELL_INT_RD, "ELL_INT_RD", 3, TP_CONST, F, true, true, {F, F, F}},
+    {OP_ELL_INT_RF, "ELL_INT_RF", 3, TP_CONST, F, true, true, {F, F, F}},
+    {OP_ELL_INT_RJ, "ELL_INT_RJ", 4, TP_CONST, F, true, true, {F, F, F, F}},
     {OP_ELL_JAC, "ELL_JAC", 2, TP_CONST, TUP, true, false, {F, F}},
     {OP_SOLVE_LINEAR_2, "SOLVE_LINEAR_2", 2, TP_CONST, TUP, true, false, {TUP, TUP}},
     {OP_SOLVE_LINEAR_3, "SOLVE_LINEAR_3", 2, TP_CONST, TUP, true, false, {TUP, TUP}},

@@ -605,9 +605,7 @@ static bool host_can_eval(const Rhs *r) {
         switch (r->op->id) {
         case OP_ORIG_VAL: case OP_APPLY_CURVE: case OP_APPLY_GRADIENT:
         case OP_GAMMA: case OP_BETA: case OP_C_GAMMA:
-        case OP_ELL_INT_K_COMP: case OP_ELL_INT_E_COMP: case OP_ELL_INT_F: case OP_ELL_INT_E: case OP_ELL_INT_P:
-        case OP_ELL_INT_D: case OP_ELL_INT_RC: case OP_ELL_INT_RD: case OP_ELL_INT_RF: case OP_ELL_INT_RJ:
-        case OP_ELL_JAC: case OP_SOLVE_LINEAR_2: case OP_SOLVE_LINEAR_3: case OP_SOLVE_POLY_2: case OP_SOLVE_POLY_3:
+        case OP_SOLVE_LINEAR_2: case OP_SOLVE_LINEAR_3: case OP_SOLVE_POLY_2: case OP_SOLVE_POLY_3:
         case OP_LIBNOISE_PERLIN: case OP_LIBNOISE_BILLOW: case OP_LIBNOISE_RIDGED_MULTI: case OP_LIBNOISE_VORONOI:
         case OP_TREE_VECTOR_NTH: case OP_SET_TREE_VECTOR_NTH:
             return false;

@@ -61,6 +61,7 @@ MM_DEV void mm_pixel_coords(int &col, int &row) {
 #endif
 }
 #include "mm_types.h"
+#include "mm_elliptic.h"
 
 template <int N> struct mm_tup { float v[N]; };
 
@@ -148,6 +149,25 @@ MM_DEV float mm_rand(unsigned &state, float a, float b) {
     double u = (double)w * (1.0 / 4294967296.0);
     return (float)((double)a + ((double)b - (double)a) * u);
 }
+// GSL elliptic functions (opmacros.h:101-125), see mm_elliptic.h; double inside, float at the boundary
+MM_DEV float mm_ell_int_k_comp(float k) { return (float)mm_ellint_kcomp((double)k); }
+MM_DEV float mm_ell_int_e_comp(float k) { return (float)mm_ellint_ecomp((double)k); }
+MM_DEV float mm_ell_int_f(float phi, float k) { return (float)mm_ellint_f((double)phi, (double)k); }
+MM_DEV float mm_ell_int_e(float phi, float k) { return (float)mm_ellint_e((double)phi, (double)k); }
+MM_DEV float mm_ell_int_p(float phi, float k, float n) { return (float)mm_ellint_p((double)phi, (double)k, (double)n); }
+MM_DEV float mm_ell_int_d(float phi, float k) { return (float)mm_ellint_d((double)phi, (double)k); }
+MM_DEV float mm_ell_int_rc(float x, float y) { return (float)mm_ellint_rc((double)x, (double)y); }
+MM_DEV float mm_ell_int_rd(float x, float y, float z) { return (float)mm_ellint_rd((double)x, (double)y, (double)z); }
+MM_DEV float mm_ell_int_rf(float x, float y, float z) { return (float)mm_ellint_rf((double)x, (double)y, (double)z); }
+MM_DEV float mm_ell_int_rj(float x, float y, float z, float p) { return (float)mm_ellint_rj((double)x, (double)y, (double)z, (double)p); }
+MM_DEV mm_tup<3> mm_ell_jac(float u, float m) {
+    double sn, cn, dn;
+    mm_elljac((double)u, (double)m, &sn, &cn, &dn);
+    mm_tup<3> r;
+    r.v[0] = (float)sn; r.v[1] = (float)cn; r.v[2] = (float)dn;
+    return r;
+}
+
 // gsl_linalg_HH_solve (GSL, third-party, absent) solves A x = b by Householder; restated with Cramer's rule in
 // double.  PARITY UNPINNED (no reference test divides by a matrix).  A singular matrix gives 0.
 MM_DEV mm_tup<2> mm_solve_linear_2(mm_tup<4> m, mm_tup<2> v) {

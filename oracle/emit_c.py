@@ -189,7 +189,7 @@ class Emitter:
                 return "((return_tuple = (%s)), 0)" % args[0]
             if name in ("SOLVE_LINEAR_2", "SOLVE_LINEAR_3"):
                 return "mmo_solve_linear_%s(%s, pools)" % (name[-1], ",".join(args))
-            if name.startswith("ELL_") or name.startswith("SOLVE_") or name.endswith("TREE_VECTOR_NTH"):
+            if name.startswith("SOLVE_") or name.endswith("TREE_VECTOR_NTH"):
                 return "mmo_unsupported_op(\"%s\")" % name
             if name == "RAND":
                 return "mmo_rand(%s)" % ",".join(args)

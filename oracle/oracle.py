@@ -22,7 +22,7 @@ from . import emit_c
 HERE = os.path.dirname(os.path.abspath(__file__))
 RUNTIME_DIR = os.path.join(HERE, "runtime")
 BUILD_DIR = os.path.join(HERE, "_build")
-RUNTIME_SOURCES = ["images.c", "driver.c", "gauss.c", "noise.c", "spec_funcs.c", "convolve.c"]
+RUNTIME_SOURCES = ["images.c", "driver.c", "gauss.c", "noise.c", "spec_funcs.c", "elliptic.c", "convolve.c"]
 CGEN_CC = ["gcc", "-O2", "-c", "-fPIC"]  # reference Makefile:58
 CGEN_LD = ["gcc", "-shared"]             # reference Makefile:59
 

@@ -21,6 +21,7 @@
 #define MMO_RUNTIME_H
 
 #include <complex.h>
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -194,6 +195,30 @@ double mmo_beta(double a, double b);
 float _Complex mmo_cgamma(float _Complex z);
 #define GAMMA(a) (((a) > 171.0) ? 0.0 : mmo_gamma((a)))
 #define gsl_sf_beta(a, b) mmo_beta((a), (b))
+/* elliptics (opmacros.h:101-125), see elliptic.c */
+double mmo_ellint_Kcomp(double k);
+double mmo_ellint_Ecomp(double k);
+double mmo_ellint_F(double phi, double k);
+double mmo_ellint_E(double phi, double k);
+double mmo_ellint_P(double phi, double k, double n);
+double mmo_ellint_D(double phi, double k);
+double mmo_ellint_RC(double x, double y);
+double mmo_ellint_RD(double x, double y, double z);
+double mmo_ellint_RF(double x, double y, double z);
+double mmo_ellint_RJ(double x, double y, double z, double p);
+void mmo_elljac(double u, double m, double *sn, double *cn, double *dn);
+float *mmo_ell_jac_tuple(float u, float m, struct mmo_pools *pools);
+#define ELL_INT_K_COMP(k) mmo_ellint_Kcomp((k))
+#define ELL_INT_E_COMP(k) mmo_ellint_Ecomp((k))
+#define ELL_INT_F(phi, k) mmo_ellint_F((phi), (k))
+#define ELL_INT_E(phi, k) mmo_ellint_E((phi), (k))
+#define ELL_INT_P(phi, k, n) mmo_ellint_P((phi), (k), (n))
+#define ELL_INT_D(phi, k, n) mmo_ellint_D((phi), (k))
+#define ELL_INT_RC(x, y) mmo_ellint_RC((x), (y))
+#define ELL_INT_RD(x, y, z) mmo_ellint_RD((x), (y), (z))
+#define ELL_INT_RF(x, y, z) mmo_ellint_RF((x), (y), (z))
+#define ELL_INT_RJ(x, y, z, p) mmo_ellint_RJ((x), (y), (z), (p))
+#define ELL_JAC(u, m) mmo_ell_jac_tuple((u), (m), pools)
 #define cgamma(z) mmo_cgamma((z))
 
 /* GSL's gsl_linalg_HH_solve is absent: Cramer's rule in double (spec_funcs.c), parity unpinned */

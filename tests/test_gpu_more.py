@@ -245,3 +245,59 @@ def test_gaussian_blur_device_bit_exact_floats(w, h, sh, sv):
     rc = mb.lib().mmb_gaussian_blur_device(0, src.data_ptr(), src.data_ptr(), w, h, sh, sv, None)
     assert rc == 0, mb._err()
     assert np.array_equal(src.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+ELL_FILTERS = {
+    "complete_and_legendre": """filter ell ()
+        k = x * 0.95; phi = y * 5;
+        rgba:[ell_int_Kcomp(k) / 4, ell_int_Ecomp(k) / 2, ell_int_F(phi, k) / 12 + 0.5, ell_int_E(phi, k) / 12 + 0.5]
+    end""",
+    "third_kind_and_carlson": """filter ell ()
+        k = x * 0.9; phi = y * 4; u = x + 1.2; v = y + 1.3;
+        rgba:[ell_int_P(phi, k, 0.4) / 10 + 0.5, ell_int_D(phi, k, 0) / 6 + 0.5, ell_int_RC(u, v) / 2, ell_int_RD(u, v, 1.5) / 2]
+    end""",
+    "carlson_and_jacobi": """filter ell ()
+        u = x + 1.2; v = y + 1.3; m = x * 0.45 + 0.5; w = y * 6;
+        rgba:[ell_int_RF(u, v, 0.7), ell_int_RJ(u, v, 0.7, 1.1) / 2, ell_jac_sn(w, m) / 2 + 0.5, ell_jac_cn(w, m) * ell_jac_dn(w, m) / 2 + 0.5]
+    end""",
+    "complex_jacobi": """filter ell ()
+        z = ell_jac_sn(ri:[x * 2, y * 1.5], 0.3); c = ell_jac_cn(ri:[x * 2, y * 1.5], 0.3); d = ell_jac_dn(ri:[x * 2, y * 1.5], 0.3);
+        rgba:[z[0] / 4 + 0.5, z[1] / 4 + 0.5, c[0] / 4 + 0.5, d[1] / 4 + 0.5]
+    end""",
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(ELL_FILTERS))
+def test_elliptic_functions_match_oracle(name):
+    """GSL's elliptic integrals / Jacobi functions (opmacros.h:101-125): the device restatement of GSL's algorithms against the
+    oracle's independent evaluation (AGM, tighter Carlson iterations).  Both are double inside; results narrowed to float may
+    differ at rare rounding boundaries, hence the 1-LSB allowance.  Parity with GSL itself is unpinned (no reference vector)."""
+    m = mb.Module(source=ELL_FILTERS[name])
+    inv = mb.Invocation(m, 192, 160)
+    got = inv.render(0, 0.0)
+    want = OracleFilter(m.ir).render(192, 160, {})
+    exact, le1, mx = compare_u8(got, want)
+    assert exact >= 99.5 and le1 == 100.0, "%s: %.4f %% exact, %.4f %% within 1 LSB, max %d" % (name, exact, le1, mx)
+    assert got[..., :3].std() > 1.0  # the picture is not flat
+
+
+@pytest.mark.gpu
+def test_quincuncial_matches_oracle():
+    """Map/Quincuncial.mm: the one reference example that needs ell_jac (per pixel, complex argument)."""
+    img = synthetic_rgba(256, 128)
+    m = mb.Module(source=filter_source("examples/Map/Quincuncial.mm"))
+    # the filter addresses `in` in pixels although `unit` makes its coordinates run over [-1, 1]: imageH = 2 keeps
+    # most samples inside the picture (with the default 500 nearly all fall outside and the result is black)
+    for uv in ({}, {"twoHemispheres": True, "rotatePole": 30.0}, {"Drostify": True}, {"DoubleQuinc": True}):
+        inv = mb.Invocation(m, 160, 160, antialiasing=True)
+        inv.set("in", img)
+        vals = {"in": img, "imageH": 2}
+        inv.set("imageH", 2)
+        for k, v in uv.items():
+            inv.set(k, v)
+            vals[k] = v
+        got = inv.render(0, 0.0)
+        want = OracleFilter(m.ir).render(160, 160, vals, antialiasing=True)
+        exact, le1, mx = compare_u8(got, want)
+        assert exact >= 99.9, "%r: %.4f %% exact, %.4f %% within 1 LSB, max %d" % (uv, exact, le1, mx)
