@@ -193,8 +193,8 @@ MM_DEV mm_tup<3> mm_solve_linear_3(mm_tup<9> m, mm_tup<3> v) {
 }
 
 // ---------------------------------------------------------------------- complex
-// float _Complex as float2.  Functions are evaluated in double and narrowed (the
-// host uses glibc's float complex functions, themselves accurate to < 1 ulp).
+// float _Complex as float2.  The inverse functions are evaluated in double and narrowed; the direct ones follow
+// glibc's float formulas (below).
 struct mm_cd { double re, im; };
 MM_DEV mm_cd mm_cd_of(float2 z) { mm_cd r; r.re = z.x; r.im = z.y; return r; }
 MM_DEV float2 mm_c_narrow(mm_cd z) { return make_float2((float)z.re, (float)z.im); }
@@ -222,41 +222,152 @@ MM_DEV float2 mm_cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + 
 MM_DEV float2 mm_csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 MM_DEV float2 mm_cneg(float2 a) { return make_float2(-a.x, -a.y); }
 MM_DEV float2 mm_cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-MM_DEV float2 mm_csqrt(float2 z) { return mm_c_narrow(mm_cd_sqrt(mm_cd_of(z))); }
+// The reference calls glibc's FLOAT complex functions (ops.lisp:196-213: csqrtf, csinf, ..., cpowf).  Those work in
+// float arithmetic on top of the float libm primitives, so the functions below follow glibc's formulas
+// (math/s_c*_template.c) step by step in float, with each primitive (sinf, coshf, logf, hypotf, atan2f ...) evaluated in
+// double and narrowed, i.e. correctly rounded.  glibc's own primitives are correctly rounded for 74 % (sinhf) to 100 %
+// (hypotf, sqrtf) of arguments, so results agree with the host's to the bit in most cases and to 1 ulp otherwise.
+// Arguments beyond glibc's overflow guards (|x| > 44 or 88) and non-finite ones take the plain double formula.
+#define MM_FLT_MIN 1.17549435e-38f
+#define MM_FLT_EPSILON 1.19209290e-07f
+MM_DEV bool mm_c_finite(float2 z) { return isfinite(z.x) && isfinite(z.y); }
+MM_DEV float mm_cr_sinh(float x) { return (float)sinh((double)x); }
+MM_DEV float mm_cr_cosh(float x) { return (float)cosh((double)x); }
+MM_DEV void mm_cr_sincos(float x, float &s, float &c) {  // glibc: sincosf unless |x| <= FLT_MIN
+    if (fabsf(x) > MM_FLT_MIN) { double ds, dc; sincos((double)x, &ds, &dc); s = (float)ds; c = (float)dc; }
+    else { s = x; c = 1.0f; }
+}
+MM_DEV float2 mm_csqrt(float2 z) {
+    // s_csqrt_template.c; the range-scaling branches (|z| > FLT_MAX/4, subnormal parts) take the double formula
+    const float ax = fabsf(z.x), ay = fabsf(z.y);
+    if (!mm_c_finite(z) || ax > 8.5e37f || ay > 8.5e37f || (ax < 2.0f * MM_FLT_MIN && ax != 0.0f) || (ay < 2.0f * MM_FLT_MIN && ay != 0.0f))
+        return mm_c_narrow(mm_cd_sqrt(mm_cd_of(z)));
+    if (z.y == 0.0f) {
+        if (z.x < 0.0f) return make_float2(0.0f, copysignf(__fsqrt_rn(-z.x), z.y));
+        return make_float2(fabsf(__fsqrt_rn(z.x)), copysignf(0.0f, z.y));
+    }
+    if (z.x == 0.0f) {
+        const float r = __fsqrt_rn(__fmul_rn(0.5f, ay));
+        return make_float2(r, copysignf(r, z.y));
+    }
+    const float d = mm_hypot(z.x, z.y);
+    float r, sgn;
+    if (z.x > 0.0f) {
+        r = __fsqrt_rn(__fmul_rn(0.5f, __fadd_rn(d, z.x)));
+        sgn = __fmul_rn(0.5f, __fdiv_rn(z.y, r));
+    } else {
+        sgn = __fsqrt_rn(__fmul_rn(0.5f, __fsub_rn(d, z.x)));
+        r = fabsf(__fmul_rn(0.5f, __fdiv_rn(z.y, sgn)));
+    }
+    return make_float2(r, copysignf(sgn, z.y));
+}
 MM_DEV float2 mm_cexp(float2 z) {
     // glibc cexpf: expf(re) * (cosf(im), sinf(im)), each factor rounded to float first
     float e = mm_exp(z.x), s = mm_sin(z.y), c = mm_cos(z.y);
     return make_float2(e * c, e * s);
 }
-MM_DEV float2 mm_clog(float2 z) { return mm_c_narrow(mm_cd_log(mm_cd_of(z))); }
+MM_DEV float2 mm_clog(float2 z) {
+    // s_clog_template.c without its scaling of huge / subnormal arguments
+    float ax = fabsf(z.x), ay = fabsf(z.y);
+    if (!mm_c_finite(z) || (ax == 0.0f && ay == 0.0f) || ax > 1.7e38f || ay > 1.7e38f || (ax < MM_FLT_MIN && ay < MM_FLT_MIN))
+        return mm_c_narrow(mm_cd_log(mm_cd_of(z)));
+    if (ax < ay) { const float t = ax; ax = ay; ay = t; }
+    float re;
+    if (ax == 1.0f) re = __fmul_rn((float)log1p((double)__fmul_rn(ay, ay)), 0.5f);
+    else if (ax > 1.0f && ax < 2.0f && ay < 1.0f) {
+        float d2m1 = __fmul_rn(__fsub_rn(ax, 1.0f), __fadd_rn(ax, 1.0f));
+        if (ay >= MM_FLT_EPSILON) d2m1 = __fadd_rn(d2m1, __fmul_rn(ay, ay));
+        re = __fmul_rn((float)log1p((double)d2m1), 0.5f);
+    } else if (ax < 1.0f && ax >= 0.5f && ay < MM_FLT_EPSILON / 2.0f) {
+        const float d2m1 = __fmul_rn(__fsub_rn(ax, 1.0f), __fadd_rn(ax, 1.0f));
+        re = __fmul_rn((float)log1p((double)d2m1), 0.5f);
+    } else if (ax < 1.0f && ax >= 0.5f && __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)) >= 0.5f) {
+        // __x2y2m1f: x^2 + y^2 - 1 evaluated exactly, rounded once (exact in double for float inputs)
+        const double d = __dsub_rn(__dadd_rn(__dmul_rn((double)ax, (double)ax), __dmul_rn((double)ay, (double)ay)), 1.0);
+        re = __fmul_rn((float)log1p((double)(float)d), 0.5f);
+    } else
+        re = (float)log((double)mm_hypot(ax, ay));
+    return make_float2(re, (float)atan2((double)z.y, (double)z.x));
+}
 MM_DEV float mm_carg(float2 z) { return mm_atan2(z.y, z.x); }
 MM_DEV float2 mm_cpow(float2 a, float2 b) {
     // glibc cpowf(x, c) = cexpf(c * clogf(x)) in float complex arithmetic
     float2 l = mm_clog(a);
     return mm_cexp(mm_cmul(b, l));
 }
+// cosh / sinh pair of glibc's ccoshf and csinhf for a finite argument with |re| <= 88
+MM_DEV float2 mm_ccosh_core(float re, float im) {
+    float s, c;
+    mm_cr_sincos(im, s, c);
+    return make_float2(__fmul_rn(mm_cr_cosh(re), c), __fmul_rn(mm_cr_sinh(re), s));
+}
+MM_DEV float2 mm_csinh_core(float re, float im) {
+    float s, c;
+    mm_cr_sincos(im, s, c);
+    return make_float2(__fmul_rn(mm_cr_sinh(re), c), __fmul_rn(mm_cr_cosh(re), s));
+}
 MM_DEV float2 mm_csin(float2 z) {
+    if (mm_c_finite(z) && fabsf(z.y) <= 88.0f) {  // s_csin_template.c
+        float s, c;
+        mm_cr_sincos(fabsf(z.x), s, c);
+        if (signbit(z.x)) s = -s;
+        return make_float2(__fmul_rn(mm_cr_cosh(z.y), s), __fmul_rn(mm_cr_sinh(z.y), c));
+    }
     double s, c; sincos((double)z.x, &s, &c);
     return make_float2((float)(s * cosh((double)z.y)), (float)(c * sinh((double)z.y)));
 }
 MM_DEV float2 mm_ccos(float2 z) {
+    if (mm_c_finite(z) && fabsf(z.y) <= 88.0f) return mm_ccosh_core(-z.y, z.x);  // ccosf(z) = ccoshf(i z), s_ccos_template.c
     double s, c; sincos((double)z.x, &s, &c);
     return make_float2((float)(c * cosh((double)z.y)), (float)(-s * sinh((double)z.y)));
 }
+// tail of glibc's ctanf / ctanhf for |v| > t = 44, where cosh(v)^2 overflows: the "hyperbolic" component is +-1 and
+// the other one 4 sin cos / exp(2|v|), divided in two steps to avoid intermediate underflow (s_ctan_template.c)
+MM_DEV float mm_ctan_small_part(float sinu, float cosu, float v) {
+    const float t = 44.0f, exp_2t = (float)exp(2.0 * 44.0);
+    float r = __fmul_rn(__fmul_rn(4.0f, sinu), cosu);
+    v = __fsub_rn(fabsf(v), t);
+    r = __fdiv_rn(r, exp_2t);
+    if (v > t) r = __fdiv_rn(r, exp_2t);
+    else r = __fdiv_rn(r, (float)exp((double)__fmul_rn(2.0f, v)));
+    return r;
+}
 MM_DEV float2 mm_ctan(float2 z) {
+    if (mm_c_finite(z)) {  // s_ctan_template.c
+        float sinrx, cosrx, sinhix, coshix, den;
+        mm_cr_sincos(z.x, sinrx, cosrx);
+        if (fabsf(z.y) > 44.0f) return make_float2(mm_ctan_small_part(sinrx, cosrx, z.y), copysignf(1.0f, z.y));
+        if (fabsf(z.y) > MM_FLT_MIN) { sinhix = mm_cr_sinh(z.y); coshix = mm_cr_cosh(z.y); }
+        else { sinhix = z.y; coshix = 1.0f; }
+        if (fabsf(sinhix) > __fmul_rn(fabsf(cosrx), MM_FLT_EPSILON)) den = __fadd_rn(__fmul_rn(cosrx, cosrx), __fmul_rn(sinhix, sinhix));
+        else den = __fmul_rn(cosrx, cosrx);
+        return make_float2(__fdiv_rn(__fmul_rn(sinrx, cosrx), den), __fdiv_rn(__fmul_rn(sinhix, coshix), den));
+    }
     double s, c; sincos(2.0 * (double)z.x, &s, &c);
     double d = c + cosh(2.0 * (double)z.y);
     return make_float2((float)(s / d), (float)(sinh(2.0 * (double)z.y) / d));
 }
 MM_DEV float2 mm_csinh(float2 z) {
+    if (mm_c_finite(z) && fabsf(z.x) <= 88.0f) return mm_csinh_core(z.x, z.y);  // s_csinh_template.c
     double s, c; sincos((double)z.y, &s, &c);
     return make_float2((float)(sinh((double)z.x) * c), (float)(cosh((double)z.x) * s));
 }
 MM_DEV float2 mm_ccosh(float2 z) {
+    if (mm_c_finite(z) && fabsf(z.x) <= 88.0f) return mm_ccosh_core(z.x, z.y);  // s_ccosh_template.c
     double s, c; sincos((double)z.y, &s, &c);
     return make_float2((float)(cosh((double)z.x) * c), (float)(sinh((double)z.x) * s));
 }
 MM_DEV float2 mm_ctanh(float2 z) {
+    if (mm_c_finite(z)) {  // s_ctanh_template.c
+        float sinix, cosix, sinhrx, coshrx, den;
+        mm_cr_sincos(z.y, sinix, cosix);
+        if (fabsf(z.x) > 44.0f) return make_float2(copysignf(1.0f, z.x), mm_ctan_small_part(sinix, cosix, z.x));
+        if (fabsf(z.x) > MM_FLT_MIN) { sinhrx = mm_cr_sinh(z.x); coshrx = mm_cr_cosh(z.x); }
+        else { sinhrx = z.x; coshrx = 1.0f; }
+        if (fabsf(sinhrx) > __fmul_rn(fabsf(cosix), MM_FLT_EPSILON)) den = __fadd_rn(__fmul_rn(sinhrx, sinhrx), __fmul_rn(cosix, cosix));
+        else den = __fmul_rn(cosix, cosix);
+        return make_float2(__fdiv_rn(__fmul_rn(sinhrx, coshrx), den), __fdiv_rn(__fmul_rn(sinix, cosix), den));
+    }
     double s, c; sincos(2.0 * (double)z.y, &s, &c);
     double d = cosh(2.0 * (double)z.x) + c;
     return make_float2((float)(sinh(2.0 * (double)z.x) / d), (float)(s / d));

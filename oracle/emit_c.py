@@ -280,7 +280,23 @@ PROLOGUE = """/* generated by oracle/emit_c.py -- ORACLE, test infrastructure on
 #include <stdio.h>
 static int mmo_unsupported_op(const char *n) { fprintf(stderr, "oracle: op %s is not supported\\n", n); abort(); return 0; }
 static mmo_image *mmo_unsupported_native(const char *n) { fprintf(stderr, "oracle: native filter %s is not supported\\n", n); abort(); return 0; }
-static double mmo_rand(double a, double b) { return a + (b - a) * (rand() / (RAND_MAX + 1.0)); }
+/* RAND: the reference draws from glib's global generator (opmacros.h:127), which no two runs reproduce.  The oracle uses
+ * the product's counter-based generator (seeded per pixel from column, row and frame; PCG output function) so that filters
+ * calling rand() can still be compared pixel by pixel.  PARITY UNPINNED against the reference by nature. */
+static unsigned mmo_rng_seed(int a, int b, int c) {
+    unsigned h = (unsigned)a * 0x9E3779B1u ^ ((unsigned)b * 0x85EBCA77u + 0x7F4A7C15u) ^ ((unsigned)c * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+static double mmo_rand_next(unsigned *state, double a, double b) {
+    unsigned w;
+    *state = *state * 747796405u + 2891336453u;
+    w = ((*state >> ((*state >> 28u) + 4u)) ^ *state) * 277803737u;
+    w = (w >> 22u) ^ w;
+    return a + (b - a) * ((double)w * (1.0 / 4294967296.0));
+}
+static int mmo_float_bits(float f) { int i; memcpy(&i, &f, 4); return i; }
+#define mmo_rand(a, b) mmo_rand_next(&mmo_rng, (a), (b))
 """
 
 FILTER_TEMPLATE = """
@@ -296,7 +312,9 @@ static void init_frame_@N@(mmo_invocation *invocation, mmo_image *closure, int f
     float R = invocation->image_R;
     mmo_userval *arguments = closure->args;
     float *return_tuple = 0;
+    unsigned mmo_rng = 0;
     (void)__canvasPixelW; (void)__canvasPixelH; (void)__renderPixelW; (void)__renderPixelH; (void)R; (void)arguments; (void)return_tuple; (void)frame; (void)t;
+    (void)mmo_rng;
 @XY_CODE@
 }
 
@@ -312,6 +330,7 @@ void calc_lines_@N@(mmo_invocation *invocation, mmo_image *closure, void *_xy_va
     int output_bpp = invocation->output_bpp;
     mmo_pools slice_pools, pixel_pools, *pools;
     int row, col;
+    unsigned mmo_rng = 0;
 @LOCAL_DECLS@
     (void)__canvasPixelW; (void)__canvasPixelH; (void)__renderPixelW; (void)__renderPixelH; (void)R; (void)arguments; (void)frame; (void)t;
     mmo_pools_init(&slice_pools);
@@ -333,6 +352,7 @@ void calc_lines_@N@(mmo_invocation *invocation, mmo_image *closure, void *_xy_va
             float x = CALC_VIRTUAL_X(col + region_x, frame_render_width, sampling_offset_x);
             (void)x;
             mmo_pools_reset(pools);
+            mmo_rng = mmo_rng_seed(col + region_x, row + region_y, frame);
 @PIXEL_CODE@
             if (floatmap)
             {
@@ -381,6 +401,7 @@ static float *filter_@N@(mmo_invocation *invocation, mmo_image *closure, float x
     mmo_userval *arguments = closure->args;
     float *return_tuple = 0;
     xy_vars_@N@ *xy_vars;
+    unsigned mmo_rng = mmo_rng_seed(mmo_float_bits(x), mmo_float_bits(y), mmo_float_bits(t));
 @LOCAL_DECLS@
     (void)__canvasPixelW; (void)__canvasPixelH; (void)__renderPixelW; (void)__renderPixelH; (void)R; (void)arguments; (void)frame;
     if (closure->xy_vars == 0)

@@ -301,3 +301,29 @@ def test_quincuncial_matches_oracle():
         want = OracleFilter(m.ir).render(160, 160, vals, antialiasing=True)
         exact, le1, mx = compare_u8(got, want)
         assert exact >= 99.9, "%r: %.4f %% exact, %.4f %% within 1 LSB, max %d" % (uv, exact, le1, mx)
+
+
+def _all_example_filters():
+    import glob
+    import os
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "filters")
+    return sorted(os.path.relpath(p, root) for p in glob.glob(os.path.join(root, "examples", "**", "*.mm"), recursive=True))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rel", _all_example_filters())
+def test_every_example_filter_matches_oracle(rel):
+    """All 189 filters of the reference's examples/ tree (80 of them also have golden pictures, test_gpu_parity.py), default
+    arguments, synthetic input images, 96x96 with antialiasing at t = 0.25: CUDA path through the C ABI against the oracle."""
+    img = synthetic_rgba(96, 96)
+    m = mb.Module(source=filter_source(rel))
+    inv = mb.Invocation(m, 96, 96, antialiasing=True)
+    vals = {}
+    for name, kind, _lo, _hi, _default in m.uservals():
+        if kind == mb.USERVAL_IMAGE:
+            inv.set(name, img)
+            vals[name] = img
+    got = inv.render(0, 0.25)
+    want = OracleFilter(m.ir).render(96, 96, vals, t=0.25, antialiasing=True)
+    exact, le1, mx = compare_u8(got, want)
+    assert exact >= 99.9, "%s: %.4f %% exact, %.4f %% within 1 LSB, max %d" % (rel, exact, le1, mx)

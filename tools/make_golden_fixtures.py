@@ -40,11 +40,14 @@ for line in open(os.path.join(REF, "run_tests.sh")):
         uservals[k] = float(v) if "." in v else int(v)
     manifest.append({"kind": m.group(1), "script": rel, "golden": golden, "uservals": uservals,
                      "cmdline": "mathmap -i -f %s %s%s OUT.png" % (script, "-s 256x256 " if m.group(1) == "render" else "-Din=marlene.png ", args)})
-# example filters the parity tests render although the reference's test list has no golden picture for them
-for rel in ["examples/Map/Quincuncial.mm"]:
+# every example filter: the reference's test list has golden pictures for 80 of them, the parity tests render the
+# rest too (CUDA path against the oracle)
+import glob
+for src in sorted(glob.glob("/root/reference/examples/**/*.mm", recursive=True)):
+    rel = os.path.relpath(src, "/root/reference")
     dst = os.path.join(OUT, "filters", rel)
     os.makedirs(os.path.dirname(dst), exist_ok=True)
-    shutil.copyfile(os.path.join("/root/reference", rel), dst)
+    shutil.copyfile(src, dst)
 shutil.copyfile(os.path.join(REF, "marlene.png"), os.path.join(OUT, "png", "marlene.png"))
 json.dump(manifest, open(os.path.join(OUT, "manifest.json"), "w"), indent=1)
 print(len(manifest), "golden vectors")
