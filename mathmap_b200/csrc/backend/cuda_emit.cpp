@@ -118,8 +118,10 @@ struct Emitter {
         case T_CURVE: return "const float *";
         case T_GRADIENT: return "const mm_color *";
         case T_IMAGE: return "int";
-        case T_TUPLE: return "mm_tup<" + std::to_string(std::max(1, cv->tuple_len)) + ">";
-        default: unsupported("tree vectors (computed tuple subscripts)");
+        case T_TUPLE:
+        case T_TREE_VECTOR:  // the reference's persistent tree (tree_vectors.c) is a value type here: a register / local array
+            return "mm_tup<" + std::to_string(std::max(1, cv->tuple_len)) + ">";
+        default: unsupported("internal error: value of unknown type");
         }
     }
 
@@ -134,7 +136,7 @@ struct Emitter {
             }
         }
         const Value *v = p.value;
-        if (v->index < 0) return v->cv->type == T_TUPLE ? ctype(v->cv) + "{}" : (v->cv->type == T_COMPLEX ? "make_float2(0.f, 0.f)" : "0");
+        if (v->index < 0) return (v->cv->type == T_TUPLE || v->cv->type == T_TREE_VECTOR) ? ctype(v->cv) + "{}" : (v->cv->type == T_COMPLEX ? "make_float2(0.f, 0.f)" : "0");
         if (!on_device(v->level)) {
             if (v->level == 0) {
                 if (uniform_set_p->insert(v).second) uniform_order_p->push_back(v);
@@ -179,6 +181,8 @@ struct Emitter {
         const OpInfo *op = r->op;
         auto A = [&](int i) { return prim(r->args[i]); };
         auto F = [&](int i) { return as_float(r->args[i]); };
+        // an int parameter fed a float value: C's implicit conversion (x86 truncation semantics)
+        auto I = [&](int i) { return ptype(r->args[i]) == T_FLOAT ? "mm_f2i(" + prim(r->args[i]) + ")" : prim(r->args[i]); };
         auto Z = [&](int i) { return as_complex(r->args[i]); };
         Type mx = T_INT;
         for (auto &a : r->args) mx = std::max(mx, ptype(a));
@@ -253,6 +257,8 @@ struct Emitter {
         case OP_BLUE: return "mm_blue(" + A(0) + ")";
         case OP_ALPHA: return "mm_alpha(" + A(0) + ")";
         case OP_TUPLE_NTH: return A(0) + ".v[" + A(1) + "]";
+        case OP_TREE_VECTOR_NTH: return "mm_tree_vector_nth(" + I(0) + ", " + A(1) + ")";  // opmacros.h:189
+        case OP_SET_TREE_VECTOR_NTH: return "mm_set_tree_vector_nth(" + I(0) + ", " + A(1) + ", " + F(2) + ")";  // opmacros.h:190
         case OP_COMPLEX: return "mm_complex(" + F(0) + ", " + F(1) + ")";
         case OP_C_REAL: return Z(0) + ".x";
         case OP_C_IMAG: return Z(0) + ".y";
@@ -308,7 +314,8 @@ struct Emitter {
         case RHS_PRIMARY: return prim(r->prim);
         case RHS_INTERNAL: return internal(r->internal);
         case RHS_OP: return op_expr(r, dest ? dest->type : T_INT);
-        case RHS_TUPLE: {
+        case RHS_TUPLE:
+        case RHS_TREE_VECTOR: {
             std::string s = "mm_tup<" + std::to_string(dest ? std::max(1, dest->tuple_len) : (int)r->args.size()) + ">{{";
             for (size_t i = 0; i < r->args.size(); ++i) s += (i ? ", " : "") + as_float(r->args[i]);
             return s + "}}";
@@ -326,7 +333,7 @@ struct Emitter {
             return s;
         }
         case RHS_CLOSURE: unsupported("an image closure that is not frame-constant");
-        default: unsupported("tree vectors (computed tuple subscripts)");
+        default: unsupported("internal error: unknown rhs kind");
         }
     }
 
@@ -441,7 +448,7 @@ size_t field_size(Type t, int tuple_len) {
     switch (t) {
     case T_COMPLEX: return 8;
     case T_CURVE: case T_GRADIENT: return 8;
-    case T_TUPLE: return 4 * (size_t)std::max(1, tuple_len);
+    case T_TUPLE: case T_TREE_VECTOR: return 4 * (size_t)std::max(1, tuple_len);
     default: return 4;
     }
 }
@@ -538,7 +545,7 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         auto ncomp = [](const Value *v) {
             switch (v->cv->type) {
             case T_COMPLEX: return 2;
-            case T_TUPLE: return std::max(1, v->cv->tuple_len);
+            case T_TUPLE: case T_TREE_VECTOR: return std::max(1, v->cv->tuple_len);
             case T_CURVE: case T_GRADIENT: return -1;
             default: return 1;
             }
@@ -554,7 +561,7 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
                 const char *elt = (v->cv->type == T_INT || v->cv->type == T_IMAGE || v->cv->type == T_NIL) ? "int" : (v->cv->type == T_COLOR ? "unsigned" : "float");
                 for (int c2 = 0; c2 < nc; ++c2) rv << "    " << elt << " *" << vn << "_" << c2 << ";\n";
                 rv_load << "    " << Emitter::ctype(v->cv) << " " << vn << ";\n";
-                if (v->cv->type == T_TUPLE) {
+                if (v->cv->type == T_TUPLE || v->cv->type == T_TREE_VECTOR) {
                     for (int c2 = 0; c2 < nc; ++c2) {
                         rv_load << "    " << vn << ".v[" << c2 << "] = __ldg(RV." << vn << "_" << c2 << " + row);\n";
                         rv_store << "    RV." << vn << "_" << c2 << "[row] = " << vn << ".v[" << c2 << "];\n";

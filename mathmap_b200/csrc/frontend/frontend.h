@@ -42,6 +42,7 @@ struct Expr {
     std::vector<Expr *> args;          // func args / tuple elems / closure args / subscripts
     Expr *a = nullptr, *b = nullptr, *c = nullptr;  // generic children
     int tagnum = 0;                    // cast
+    bool vector_select = false;        // EX_SELECT with a computed subscript (compiler.c:2543-2553)
 };
 
 class Gen;  // IR generation context (irgen.h)

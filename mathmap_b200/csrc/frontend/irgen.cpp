@@ -480,7 +480,51 @@ static bool single_const(const Expr *e, int *iv) {
     return false;
 }
 
+// compiler.c:2521-2570: a variable read or written through a subscript that is not a literal becomes a "vector
+// variable"; a select with such a subscript is marked so that its tuple operand is materialised as a tree vector
+static void find_vector_variables(Expr *t) {
+    if (!t) return;
+    switch (t->kind) {
+    case EX_SELECT:
+        find_vector_variables(t->a);
+        for (Expr *sub : t->args) {
+            int dummy;
+            find_vector_variables(sub);
+            if (!single_const(sub, &dummy)) {
+                t->vector_select = true;
+                if (t->a->kind == EX_VARIABLE) t->a->var->is_vector = true;
+            }
+        }
+        return;
+    case EX_SUB_ASSIGNMENT:
+        find_vector_variables(t->a);
+        for (Expr *sub : t->args) {
+            int dummy;
+            find_vector_variables(sub);
+            if (!single_const(sub, &dummy)) t->var->is_vector = true;
+        }
+        return;
+    default:
+        for (Expr *e : t->args) find_vector_variables(e);
+        find_vector_variables(t->a);
+        find_vector_variables(t->b);
+        find_vector_variables(t->c);
+    }
+}
+
+static CompVar *new_tree_vector_compvar(Gen &g, int length, const std::string &name) {
+    CompVar *cv = g.code.new_compvar(T_TREE_VECTOR, name);
+    cv->tuple_len = length;
+    cv->current = g.code.new_value(cv);
+    return cv;
+}
+
 static void alloc_var_compvars(Gen &g, Variable *v) {
+    if (v->is_vector) {  // compiler.c:1776-1785
+        if (v->compvars.size() != 1) v->compvars.assign(1, nullptr);
+        if (!v->compvars[0]) v->compvars[0] = new_tree_vector_compvar(g, v->length, v->name);
+        return;
+    }
     if ((int)v->compvars.size() != v->length) v->compvars.assign(v->length, nullptr);
     for (int i = 0; i < v->length; ++i)
         if (!v->compvars[i]) {
@@ -489,6 +533,27 @@ static void alloc_var_compvars(Gen &g, Variable *v) {
             cv->current = g.code.new_value(cv);
             v->compvars[i] = cv;
         }
+}
+
+// compiler.c:1838-1873
+CompVar *Gen::gen_tree_vector(Expr *tree, CompVar **dest, bool alloced) {
+    if (tree->kind == EX_VARIABLE && tree->var->is_vector) {
+        alloc_var_compvars(*this, tree->var);
+        CompVar *tv = tree->var->compvars[0];
+        for (int i = 0; i < tree->result.length; ++i) {
+            if (!alloced) dest[i] = temp(T_FLOAT);
+            assign(dest[i], rhs_op(OP_TREE_VECTOR_NTH, {ic(i), cur(tv)}));
+        }
+        return tv;
+    }
+    gen_code(tree, dest, alloced);
+    std::vector<P> args;
+    for (int i = 0; i < tree->result.length; ++i) args.push_back(cur(dest[i]));
+    CompVar *tv = new_tree_vector_compvar(*this, tree->result.length, "");
+    Rhs *r = code.new_rhs(RHS_TREE_VECTOR);
+    r->args = std::move(args);
+    assign(tv, r);
+    return tv;
 }
 
 void Gen::gen_code(Expr *tree, CompVar **dest, bool alloced) {
@@ -507,19 +572,33 @@ void Gen::gen_code(Expr *tree, CompVar **dest, bool alloced) {
         break;
     case EX_SELECT: {
         std::vector<CompVar *> temps(tree->a->result.length, nullptr);
-        gen_code(tree->a, temps.data(), false);
+        CompVar *tree_vector = nullptr;
+        if (tree->vector_select) tree_vector = gen_tree_vector(tree->a, temps.data(), false);
+        else gen_code(tree->a, temps.data(), false);
         for (size_t i = 0; i < tree->args.size(); ++i) {
             int sub;
-            if (!single_const(tree->args[i], &sub))
-                gen_fail("Tuple subscripts must be constants (computed subscripts are not supported by this backend).", tree);
-            sub = std::max(0, std::min(sub, tree->a->result.length - 1));
-            if (!alloced) dest[i] = temps[sub];
-            else assign(dest[i], rhs_prim(cur(temps[sub])));
+            if (single_const(tree->args[i], &sub)) {
+                sub = std::max(0, std::min(sub, tree->a->result.length - 1));
+                if (!alloced) dest[i] = temps[sub];
+                else assign(dest[i], rhs_prim(cur(temps[sub])));
+            } else {  // compiler.c:1941-1955
+                CompVar *subscript = nullptr;
+                if (!alloced) dest[i] = temp(T_INT);
+                gen_code(tree->args[i], &subscript, false);
+                assign(dest[i], rhs_op(OP_TREE_VECTOR_NTH, {cur(subscript), cur(tree_vector)}));
+            }
         }
         break;
     }
     case EX_VARIABLE:
         alloc_var_compvars(*this, tree->var);
+        if (tree->var->is_vector) {  // compiler.c:1962-1971
+            for (int i = 0; i < tree->var->length; ++i) {
+                if (!alloced) dest[i] = temp(T_INT);
+                assign(dest[i], rhs_op(OP_TREE_VECTOR_NTH, {ic(i), cur(tree->var->compvars[0])}));
+            }
+            break;
+        }
         for (int i = 0; i < tree->var->length; ++i)
             if (!alloced) dest[i] = tree->var->compvars[i];
             else assign(dest[i], rhs_prim(cur(tree->var->compvars[i])));
@@ -533,6 +612,11 @@ void Gen::gen_code(Expr *tree, CompVar **dest, bool alloced) {
     }
     case EX_ASSIGNMENT:
         alloc_var_compvars(*this, tree->var);
+        if (tree->var->is_vector) {  // compiler.c:1995-1999
+            CompVar *tv = gen_tree_vector(tree->a, dest, alloced);
+            assign(tree->var->compvars[0], rhs_prim(cur(tv)));
+            break;
+        }
         gen_code(tree->a, tree->var->compvars.data(), true);
         for (int i = 0; i < tree->result.length; ++i)
             if (alloced) assign(dest[i], rhs_prim(cur(tree->var->compvars[i])));
@@ -544,10 +628,15 @@ void Gen::gen_code(Expr *tree, CompVar **dest, bool alloced) {
         gen_code(tree->a, temps.data(), false);
         for (size_t i = 0; i < tree->args.size(); ++i) {
             int sub;
-            if (!single_const(tree->args[i], &sub))
-                gen_fail("Tuple subscripts must be constants (computed subscripts are not supported by this backend).", tree);
-            sub = std::max(0, std::min(sub, tree->var->length - 1));
-            assign(tree->var->compvars[sub], rhs_prim(cur(temps[i])));
+            if (tree->var->is_vector) {  // compiler.c:2027-2038
+                CompVar *tv = tree->var->compvars[0], *subscript = nullptr;
+                gen_code(tree->args[i], &subscript, false);
+                assign(tv, rhs_op(OP_SET_TREE_VECTOR_NTH, {cur(subscript), cur(tv), cur(temps[i])}));
+            } else if (single_const(tree->args[i], &sub)) {
+                sub = std::max(0, std::min(sub, tree->var->length - 1));
+                assign(tree->var->compvars[sub], rhs_prim(cur(temps[i])));
+            } else
+                gen_fail("internal error: computed subscript on a variable that is not a vector variable", tree);
             if (alloced) assign(dest[i], rhs_prim(cur(temps[i])));
             else dest[i] = temps[i];
         }
@@ -659,6 +748,7 @@ Stmt *Gen::gen_filter_code(Filter *f, CompVar *tuple, const std::vector<P> *args
 
     filter = f;
     for (auto &v : f->variables) v->compvars.clear();
+    find_vector_variables(f->body);
     history = std::make_shared<InlineHistory>(InlineHistory{f, hist});
     bindings.clear();
 

@@ -102,6 +102,7 @@ class Gen {
     std::vector<Binding> bindings;
     Value *lookup_binding(int kind, const void *key);
     void gen_code(Expr *tree, CompVar **dest, bool alloced);
+    CompVar *gen_tree_vector(Expr *tree, CompVar **dest, bool alloced);
     Stmt *gen_filter_code(Filter *f, CompVar *tuple, const std::vector<P> *args, Rhs **tuple_rhs,
                           std::shared_ptr<InlineHistory> hist);
 

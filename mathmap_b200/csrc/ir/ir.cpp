@@ -222,7 +222,8 @@ Type rhs_type(const Rhs *rhs) {
 
 int tuple_length_of_rhs(const Rhs *rhs) {
     switch (rhs->kind) {
-    case RHS_TUPLE: return (int)rhs->args.size();
+    case RHS_TUPLE:
+    case RHS_TREE_VECTOR: return (int)rhs->args.size();
     case RHS_FILTER: return 4;
     case RHS_OP:
         switch (rhs->op->id) {

@@ -191,7 +191,9 @@ struct Variable {
     std::string name;
     int tag = 0, length = 0;
     std::vector<CompVar *> compvars;
-    CompVar *tree_vector = nullptr;
+    // subscripted somewhere by a computed index: held as ONE tree-vector compvar (compvars[0]) instead of one
+    // compvar per element (compiler.c:2521-2570 find_all_vector_variables)
+    bool is_vector = false;
 };
 
 struct Filter {

@@ -149,6 +149,8 @@ struct Builder {
             if ((int)x.size() - 2 != r->op->nargs) bad("wrong number of arguments for op " + x[1].atom);
         } else if (head == "tuple") {
             r = code.new_rhs(RHS_TUPLE);
+        } else if (head == "tree-vector") {
+            r = code.new_rhs(RHS_TREE_VECTOR);
         } else if (head == "closure" || head == "filter") {
             r = code.new_rhs(head == "closure" ? RHS_CLOSURE : RHS_FILTER);
             r->filter = mod.lookup_filter(x[1].atom);

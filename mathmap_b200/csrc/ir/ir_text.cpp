@@ -134,7 +134,7 @@ std::string dump_ir(const FilterCode &code) {
     for (auto &cv : code.compvars) {
         if (!live.count(&cv)) continue;
         o << "\n   (" << cv.id << " " << type_name(cv.type);
-        if (cv.type == T_TUPLE) o << " " << cv.tuple_len;
+        if (cv.type == T_TUPLE || cv.type == T_TREE_VECTOR) o << " " << cv.tuple_len;
         o << ")";
     }
     o << ")\n  (code\n";

@@ -570,10 +570,11 @@ void propagate_types(FilterCode &code) {
         changed = false;
         walk(code.first, [&](Stmt *s) {
             if (s->kind != ST_ASSIGN && s->kind != ST_PHI) return;
-            if (s->lhs->cv->type != T_TUPLE) return;
+            if (s->lhs->cv->type != T_TUPLE && s->lhs->cv->type != T_TREE_VECTOR) return;
             auto len_of = [&](Rhs *r) {
                 if (!r) return 0;
                 if (r->kind == RHS_PRIMARY) return r->prim.is_const ? 0 : r->prim.value->cv->tuple_len;
+                if (r->kind == RHS_OP && r->op->id == OP_SET_TREE_VECTOR_NTH) return r->args[1].is_const ? 0 : r->args[1].value->cv->tuple_len;
                 return tuple_length_of_rhs(r);
             };
             int l = std::max(len_of(s->rhs), s->kind == ST_PHI ? len_of(s->rhs2) : 0);

@@ -65,6 +65,19 @@ MM_DEV void mm_pixel_coords(int &col, int &row) {
 
 template <int N> struct mm_tup { float v[N]; };
 
+// Tree vectors (tree_vectors.c:83-146): a tuple indexed by a computed subscript.  The reference keeps a persistent
+// tree so that an update shares structure; the semantics are those of a value: get clamps the index into
+// [0, length), set returns a copy with one element replaced.
+template <int N> MM_DEV float mm_tree_vector_nth(int index, const mm_tup<N> &tv) {
+    index = index < 0 ? 0 : (index >= N ? N - 1 : index);
+    return tv.v[index];
+}
+template <int N> MM_DEV mm_tup<N> mm_set_tree_vector_nth(int index, mm_tup<N> tv, float value) {
+    index = index < 0 ? 0 : (index >= N ? N - 1 : index);
+    tv.v[index] = value;
+    return tv;
+}
+
 // ---------------------------------------------------------------- conversions
 // float/double -> int with x86 cvttss2si semantics (out of range and NaN give
 // INT_MIN), which is what the reference's C casts do on its host.

@@ -55,8 +55,11 @@ class Filter:
         for u in sx[3][1:]:
             self.uservals.append((u[0], u[1][1], u[2:]))
         self.vartypes = {}
+        self.varlengths = {}  # tuple / tree_vector compvars: element count
         for v in sx[4][1:]:
             self.vartypes[int(v[0])] = v[1]
+            if len(v) > 2:
+                self.varlengths[int(v[0])] = int(v[2])
         self.code = sx[5][1:]
         self.cname = re.sub(r"[^A-Za-z0-9_]", "_", self.name)
 
@@ -189,12 +192,20 @@ class Emitter:
                 return "((return_tuple = (%s)), 0)" % args[0]
             if name in ("SOLVE_LINEAR_2", "SOLVE_LINEAR_3"):
                 return "mmo_solve_linear_%s(%s, pools)" % (name[-1], ",".join(args))
-            if name.startswith("SOLVE_") or name.endswith("TREE_VECTOR_NTH"):
+            if name in ("TREE_VECTOR_NTH", "SET_TREE_VECTOR_NTH"):
+                # tree_vectors.c:83-146 keeps a persistent tree; as a value it is an array whose length travels with
+                # the compvar type: get clamps the index, set copies and replaces one element
+                tv = r[3]
+                length = self.f.varlengths[int(tv[1:].split(".")[0])]
+                if name == "TREE_VECTOR_NTH":
+                    return "mmo_tree_vector_get(%s, %d, %s)" % (args[1], length, args[0])
+                return "mmo_tree_vector_set(pools, %s, %d, %s, %s)" % (args[1], length, args[0], args[2])
+            if name.startswith("SOLVE_"):
                 return "mmo_unsupported_op(\"%s\")" % name
             if name == "RAND":
                 return "mmo_rand(%s)" % ",".join(args)
             return "%s(%s)" % (name, ",".join(args))
-        if head == "tuple":
+        if head in ("tuple", "tree-vector"):
             n = len(r) - 1
             body = "".join("tuple[%d] = %s; " % (i, self.prim(a)) for i, a in enumerate(r[1:]))
             return "({ float *tuple = ALLOC_TUPLE(%d); %stuple; })" % (n, body)
@@ -296,6 +307,18 @@ static double mmo_rand_next(unsigned *state, double a, double b) {
     return a + (b - a) * ((double)w * (1.0 / 4294967296.0));
 }
 static int mmo_float_bits(float f) { int i; memcpy(&i, &f, 4); return i; }
+static float mmo_tree_vector_get(const float *tv, int length, int index) {
+    if (tv == 0) return 0.0f; /* never assigned */
+    if (index < 0) index = 0; else if (index >= length) index = length - 1;
+    return tv[index];
+}
+static float *mmo_tree_vector_set(mmo_pools *pools, const float *tv, int length, int index, float value) {
+    float *copy = ALLOC_TUPLE(length);
+    if (tv) memcpy(copy, tv, sizeof(float) * length); else memset(copy, 0, sizeof(float) * length);
+    if (index < 0) index = 0; else if (index >= length) index = length - 1;
+    copy[index] = value;
+    return copy;
+}
 #define mmo_rand(a, b) mmo_rand_next(&mmo_rng, (a), (b))
 """
 

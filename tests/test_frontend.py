@@ -78,3 +78,30 @@ def test_native_filter_closure_is_frame_constant():
     ir = ir_of(filter_source("examples/Blur/Gaussian Blur.mm"))
     line = [l for l in ir.splitlines() if "(closure gaussian_blur" in l][0]
     assert re.search(r" 7 0 \(closure gaussian_blur", line)
+
+
+TREE_VECTOR_SRC = """filter tv (int k: 0-7 (2))
+    v = rgba:[x * 0.5 + 0.5, y * 0.5 + 0.5, 0.25, 1];
+    i = floor((x + 1) * 2);
+    q = v[i];
+    w = v;
+    w[i] = 1 - q;
+    w[k] = w[k] * 0.5;
+    rgba:[w[0], w[1], w[2], v[floor(y * 3)]]
+end"""
+
+
+def test_computed_subscripts_become_tree_vectors():
+    """compiler.c:2521-2570, 1838-1873: a variable subscripted by a computed index is held as one tree-vector compvar,
+    reads are TREE_VECTOR_NTH, element stores SET_TREE_VECTOR_NTH (also for literal subscripts of such a variable)."""
+    ir = ir_of(TREE_VECTOR_SRC)
+    assert re.search(r"\(\d+ tree_vector 4\)", ir)
+    assert "(tree-vector " in ir
+    assert ir.count("(op SET_TREE_VECTOR_NTH") == 2
+    assert re.search(r"\(op TREE_VECTOR_NTH i:0 %\d+\.\d+\)", ir)
+    # a select with only literal subscripts on an ordinary variable stays element-wise
+    plain = ir_of("filter p () v = rgba:[x, y, 0, 1]; rgba:[v[1], v[0], v[2], v[3]] end")
+    assert "TREE_VECTOR" not in plain and "tree_vector" not in plain
+    # the IR text round-trips through the loader
+    m2 = mb.Module(ir=ir)
+    assert m2.ir == ir

@@ -327,3 +327,54 @@ def test_every_example_filter_matches_oracle(rel):
     want = OracleFilter(m.ir).render(96, 96, vals, t=0.25, antialiasing=True)
     exact, le1, mx = compare_u8(got, want)
     assert exact >= 99.9, "%s: %.4f %% exact, %.4f %% within 1 LSB, max %d" % (rel, exact, le1, mx)
+
+
+TREE_VECTOR_FILTERS = {
+    "select_and_store": """filter tv (int k: 0-7 (2))
+        v = rgba:[x * 0.5 + 0.5, y * 0.5 + 0.5, 0.25, 1];
+        i = floor((x + 1) * 2);
+        q = v[i];
+        w = v;
+        w[i] = 1 - q;
+        w[k] = w[k] * 0.5;
+        rgba:[w[0], w[1], w[2], v[floor(y * 3)]]
+    end""",
+    "loop_with_clamping": """filter tv ()
+        v = rgba:[0.1, 0.2, 0.3, 0.4];
+        i = 0; s = x * 0.1;
+        while i < 6 do
+            s = s + v[i - 1];
+            v[i % 4] = s * 0.3;
+            i = i + 1
+        end;
+        rgba:[v[0], v[1], s * 0.2, v[9]]
+    end""",
+    "select_from_expression": """filter tv (image in)
+        p = in(xy:[x, y]);
+        n = floor(abs(x) * 4 + t * 4);
+        c = (p * 0.5 + 0.25)[n];
+        rgba:[c, p[n + 1], p[2 - n], 1]
+    end""",
+    "float_subscript": """filter tv ()
+        v = rgba:[0.9, 0.6, 0.3, 0.1];
+        rgba:[v[x * 3], v[(y + 1) * 1.9], v[-5.5], v[(x + 2) * 30000.0 * 30000.0 * 30000.0]]
+    end""",
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(TREE_VECTOR_FILTERS))
+def test_tree_vectors_match_oracle(name):
+    """Computed tuple subscripts (tree_vectors.c, opmacros.h:188-190): index clamping, copy-on-store, float subscripts
+    truncated like the reference's C (x86 conversion: out of range gives INT_MIN, which clamps to 0)."""
+    img = synthetic_rgba(80, 64)
+    m = mb.Module(source=TREE_VECTOR_FILTERS[name])
+    inv = mb.Invocation(m, 80, 64, antialiasing=True)
+    vals = {}
+    if "image in" in TREE_VECTOR_FILTERS[name]:
+        inv.set("in", img)
+        vals["in"] = img
+    got = inv.render(0, 0.5)
+    want = OracleFilter(m.ir).render(80, 64, vals, t=0.5, antialiasing=True)
+    assert np.array_equal(got, want), "%s: %r" % (name, compare_u8(got, want))
+    assert got[..., :3].std() > 1.0
