@@ -110,7 +110,10 @@ struct mmb_invocation {
     void *default_curve = nullptr, *default_gradient = nullptr;
     cudaStream_t copy_stream = nullptr;  // device->host copies overlap the next chunk's kernel
     cudaStream_t aux_stream = nullptr;   // odd chunks render here so one chunk's tail overlaps the next chunk's head
-    cudaEvent_t order_event = nullptr;
+    cudaEvent_t order_event = nullptr;   // start of a chunked band (timed)
+    // cost of each chunk of the last chunked band (ms between consecutive completions) and the band it belongs to
+    std::vector<float> chunk_cost;
+    int cost_fr = -1, cost_lr = -1, cost_chunk_rows = -1, cost_floatmap = -1;
     std::vector<cudaEvent_t> chunk_events;
 
     void *alloc(size_t bytes) {
@@ -979,34 +982,49 @@ int mmb_calc_lines(mmb_invocation *inv, int first_row, int last_row, void *q, in
         size_t row_bytes = floatmap ? sizeof(float) * 4 * (size_t)inv->W : (size_t)inv->W * inv->bpp;
         size_t bytes = row_bytes * (size_t)(lr - fr);
         void *d = inv->ensure_staging(inv->staging, inv->staging_bytes, bytes);
-        // The band is rendered in chunks; the device->host copy of chunk i runs on a copy stream while the
+        // The band is rendered in chunks; the device->host copy of a chunk runs on a copy stream while the
         // kernels of the following chunks run (q pinned: true overlap; pageable q: still correct).  Chunks
         // alternate between two compute streams, so the last blocks of one chunk (rows of a filter differ in
         // cost) do not leave the device idle before the next chunk starts.
+        //
+        // Order: kernel then copy is a two-machine flow shop with equal copy times, so the makespan is smallest
+        // when the cheapest chunks are rendered first (Johnson's rule): the copy engine starts early and the
+        // expensive chunks at the end hide the copy backlog.  Chunk costs are measured (time between consecutive
+        // completions) and reused by the next call on the same band, e.g. the next frame of an animation; the
+        // first call renders from the outside in (top, bottom, second from top, ...).
         int rows = lr - fr;
         int chunks = 1;
         if (!inv->cfg.supersampling && bytes >= ((size_t)8 << 20)) chunks = (int)std::min<size_t>(32, std::max<size_t>(2, bytes >> 25));
         int chunk_rows = ((rows + chunks - 1) / chunks + 7) & ~7;
+        chunks = (rows + chunk_rows - 1) / chunk_rows;
         if (!inv->copy_stream) ck(cudaStreamCreateWithFlags(&inv->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
         if (!inv->aux_stream) ck(cudaStreamCreateWithFlags(&inv->aux_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        if (!inv->order_event) ck(cudaEventCreateWithFlags(&inv->order_event, cudaEventDisableTiming), "cudaEventCreate");
-        cudaStream_t main_stream = inv->stream;
-        if (chunks > 1) {  // everything queued so far (init_frame's renders and blurs) precedes the chunks on both streams
-            ck(cudaEventRecord(inv->order_event, main_stream), "cudaEventRecord");
-            ck(cudaStreamWaitEvent(inv->aux_stream, inv->order_event, 0), "cudaStreamWaitEvent");
+        if (!inv->order_event) ck(cudaEventCreate(&inv->order_event), "cudaEventCreate");
+        while ((int)inv->chunk_events.size() < chunks) {
+            cudaEvent_t e;
+            ck(cudaEventCreate(&e), "cudaEventCreate");
+            inv->chunk_events.push_back(e);
         }
-        int ci = 0;
+        std::vector<int> order(chunks);
+        const bool have_costs = inv->cost_fr == fr && inv->cost_lr == lr && inv->cost_chunk_rows == chunk_rows && inv->cost_floatmap == floatmap &&
+                                (int)inv->chunk_cost.size() == chunks;
+        if (have_costs) {
+            for (int i = 0; i < chunks; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return inv->chunk_cost[a] < inv->chunk_cost[b]; });
+        } else {
+            for (int i = 0, lo = 0, hi = chunks - 1; i < chunks; ++i) order[i] = (i & 1) ? hi-- : lo++;
+        }
+        cudaStream_t main_stream = inv->stream;
+        ck(cudaEventRecord(inv->order_event, main_stream), "cudaEventRecord");
+        // everything queued so far (init_frame's renders and blurs) precedes the chunks on both streams
+        if (chunks > 1) ck(cudaStreamWaitEvent(inv->aux_stream, inv->order_event, 0), "cudaStreamWaitEvent");
         try {
-            for (int r0 = fr; r0 < lr; r0 += chunk_rows, ++ci) {
-                int r1 = std::min(lr, r0 + chunk_rows);
+            for (int k = 0; k < chunks; ++k) {
+                const int ci = order[k];
+                const int r0 = fr + ci * chunk_rows, r1 = std::min(lr, r0 + chunk_rows);
                 char *dchunk = (char *)d + (size_t)(r0 - fr) * row_bytes;
-                inv->stream = (ci & 1) ? inv->aux_stream : main_stream;
+                inv->stream = (k & 1) ? inv->aux_stream : main_stream;
                 render_band(inv, r0, r1, dchunk, floatmap);
-                if ((int)inv->chunk_events.size() <= ci) {
-                    cudaEvent_t e;
-                    ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
-                    inv->chunk_events.push_back(e);
-                }
                 ck(cudaEventRecord(inv->chunk_events[ci], inv->stream), "cudaEventRecord");
                 ck(cudaStreamWaitEvent(inv->copy_stream, inv->chunk_events[ci], 0), "cudaStreamWaitEvent");
                 ck(cudaMemcpyAsync((char *)q + (size_t)(r0 - fr) * row_bytes, dchunk, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDeviceToHost,
@@ -1021,6 +1039,17 @@ int mmb_calc_lines(mmb_invocation *inv, int first_row, int last_row, void *q, in
         ck(cudaStreamSynchronize(inv->aux_stream), "cudaStreamSynchronize");
         ck(cudaStreamSynchronize(inv->copy_stream), "cudaStreamSynchronize");
         ck(cudaStreamSynchronize(inv->stream), "cudaStreamSynchronize");
+        if (chunks > 1) {
+            inv->chunk_cost.assign(chunks, 0.0f);
+            cudaEvent_t prev = inv->order_event;
+            for (int k = 0; k < chunks; ++k) {
+                float ms = 0.0f;
+                if (cudaEventElapsedTime(&ms, prev, inv->chunk_events[order[k]]) != cudaSuccess) ms = 0.0f;
+                inv->chunk_cost[order[k]] = ms > 0.0f ? ms : 0.0f;  // a chunk that finished before its predecessor: no cost of its own
+                if (ms > 0.0f) prev = inv->chunk_events[order[k]];
+            }
+            inv->cost_fr = fr; inv->cost_lr = lr; inv->cost_chunk_rows = chunk_rows; inv->cost_floatmap = floatmap;
+        }
     });
 }
 
