@@ -42,6 +42,13 @@ enum { MMB_EDGE_COLOR = 0, MMB_EDGE_WRAP = 1, MMB_EDGE_REFLECT = 2, MMB_EDGE_ROT
  */
 mmb_module *mmb_compile(const char *source);
 mmb_module *mmb_load_ir(const char *ir_text);
+/* Compositions (".mmc" designs, the composer's save format, designer/loadsave.c:30 designer_load_design): the MathMap
+ * source the reference generates for a design (designer_filter.c:278 make_filter_source_from_design); node types are
+ * looked up by the name of the main filter of the .mm / .mmc files found under filter_search_path
+ * (expression_db.c:155 read_expression_db).  The string is malloc'd: release it with mmb_free_string. */
+char *mmb_design_to_source(const char *design_text, const char *filter_search_path);
+void mmb_free_string(char *s);
+mmb_module *mmb_compile_design(const char *design_text, const char *filter_search_path);
 void mmb_module_free(mmb_module *m); /* unload_c_code, backends/cc.c:761 */
 const char *mmb_module_ir(const mmb_module *m);          /* optimised IR as text */
 const char *mmb_module_cuda_source(mmb_module *m);       /* generated CUDA C for the default configuration */

@@ -38,6 +38,7 @@ def lib():
     vp, ci, cf, cc = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_char_p
     sigs = {
         "mmb_compile": (vp, [cc]), "mmb_load_ir": (vp, [cc]), "mmb_module_free": (None, [vp]),
+        "mmb_design_to_source": (vp, [cc, cc]), "mmb_free_string": (None, [vp]), "mmb_compile_design": (vp, [cc, cc]),
         "mmb_module_ir": (cc, [vp]), "mmb_module_cuda_source": (cc, [vp]), "mmb_module_main_filter_name": (cc, [vp]),
         "mmb_module_num_uservals": (ci, [vp]),
         "mmb_module_userval_info": (ci, [vp, ci, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ci), ctypes.POINTER(cf), ctypes.POINTER(cf), ctypes.POINTER(cf)]),
@@ -72,6 +73,18 @@ def _err():
     return lib().mmb_last_error().decode("utf-8", "replace")
 
 
+def design_to_source(design_text, filter_path):
+    """The MathMap source of a composition (reference: make_filter_source_from_design, designer_filter.c:278)."""
+    L = lib()
+    p = L.mmb_design_to_source(design_text.encode(), os.fsencode(filter_path))
+    if not p:
+        raise MathMapError(_err())
+    try:
+        return ctypes.string_at(p).decode()
+    finally:
+        L.mmb_free_string(p)
+
+
 class Module:
     """A compiled filter module (reference: mathmap_t after compile_mathmap, mathmap_common.c:504)."""
 
@@ -89,9 +102,16 @@ class Module:
             _lib.mmb_module_free(h)
 
     @classmethod
-    def from_file(cls, path):
+    def from_file(cls, path, filter_path=None):
+        """A `.mm` filter, or a `.mmc` composition whose node types are looked up under `filter_path`
+        (default: the directory tree the file lives in, two levels up like the reference's examples/ layout)."""
         with open(path) as f:
-            return cls(source=f.read())
+            text = f.read()
+        if path.endswith(".mmc"):
+            if filter_path is None:
+                filter_path = os.path.dirname(os.path.dirname(os.path.abspath(path)))
+            return cls(source=design_to_source(text, filter_path))
+        return cls(source=text)
 
     @property
     def ir(self):

@@ -461,10 +461,29 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
     std::set<const Filter *> called, emitted_calls;
     std::ostringstream kernels_text;
 
+    // Filters that survive optimisation as closure VALUES (RHS_CLOSURE): a closure that is sampled through ORIG_VAL in
+    // code that could not inline it (another closure's argument, a rendered closure's input) is called on the device
+    // through mm_closure_dispatch, the analogue of the reference's img->v.closure.func pointer (opmacros.h:208-209).
+    std::set<const Filter *> closure_targets;
+    {
+        std::function<void(const Stmt *)> scan = [&](const Stmt *st) {
+            for (; st; st = st->next) {
+                if (st->kind == ST_ASSIGN && st->rhs->kind == RHS_CLOSURE && st->rhs->filter->kind == FILTER_MATHMAP) closure_targets.insert(st->rhs->filter);
+                else if (st->kind == ST_IF) { scan(st->cons); scan(st->alt); }
+                else if (st->kind == ST_WHILE) scan(st->body);
+            }
+        };
+        for (auto &fp : m.mod->filters)
+            if (fp->kind == FILTER_MATHMAP) scan(m.code_for(fp.get())->first);
+    }
+    std::ostringstream dispatch;
+    int filter_index = -1;
+
     // forward declarations of callable filters are emitted once we know which are called
     std::vector<std::string> bodies;
     for (auto &fp : m.mod->filters) {
         const Filter *f = fp.get();
+        ++filter_index;
         if (f->kind != FILTER_MATHMAP) continue;
         const FilterCode *code = m.code_for(f);
         std::string name = sanitize(f->name);
@@ -507,8 +526,22 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
             row_body = er.out.str();
         }
 
+        // the closure flavour: the pixel code as a device function of (x, y, t); frame constants come from the same
+        // uniforms struct (filled by a host replay with the closure's arguments), image slots from its fields
+        const bool closure_fn = closure_targets.count(f) != 0;
+        Emitter ec(m, *code, Emitter::PIXEL_ALL, called);
+        std::vector<const Value *> closure_decls;
+        if (closure_fn) {
+            ec.uniform_set_p = &e.own_uniform_set;
+            ec.uniform_order_p = &e.own_uniform_order;
+            ec.collect_decls(code->first, closure_decls);
+            ec.emit_stmts(code->first, "    ");
+        }
+
         FilterKernel k;
         k.filter = f;
+        k.filter_index = filter_index;
+        k.closure_fn = closure_fn;
         k.kernel_name = "mm_kernel_" + name;
         // layout: 8-byte fields first, then 4-byte ones
         std::vector<const Value *> order = e.own_uniform_order;
@@ -611,6 +644,14 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         fn << body
            << "    mm_store_pixel(P, row + P.first_row, col, mm_ret);\n"
            << "}\n";
+        if (closure_fn) {  // new_template.c.in:375-422 filter_$name, with the frame constants precomputed
+            fn << "__device__ mm_tup<4> mm_closure_" << name << "(const mm_params &P, const mm_uniforms_" << name << " &U, float x, float y, float t) {\n"
+               << "    const int frame = 0;\n    (void)frame; (void)x; (void)y; (void)t;\n    mm_tup<4> mm_ret = mm_tup<4>{};\n"
+               << "    unsigned mm_rng = mm_rng_seed(__float_as_int(x), __float_as_int(y), __float_as_int(t)); (void)mm_rng;\n";
+            for (const Value *v : closure_decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
+            fn << ec.out.str() << "    return mm_ret;\n}\n";
+            dispatch << "    case " << filter_index << ": return mm_closure_" << name << "(P, *(const mm_uniforms_" << name << " *)img.data, x, y, t);\n";
+        }
         bodies.push_back(fn.str());
         src.kernels[f] = k;
     }
@@ -656,6 +697,10 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
     text << protos.str();
     for (auto &b : bodies) text << b;
     text << calls.str();
+    // declared in mm_runtime.cuh; img.data points at the closure filter's uniforms, packed by the host
+    text << "__device__ mm_tup<4> mm_closure_dispatch(const mm_params &P, const mm_image &img, float x, float y, float t) {\n"
+         << "    switch (img.closure_filter) {\n" << dispatch.str() << "    default: break;\n    }\n"
+         << "    (void)P; (void)x; (void)y; (void)t;\n    return mm_tup<4>{};\n}\n";
     src.text = text.str();
     return src;
 }

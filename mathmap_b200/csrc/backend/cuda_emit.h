@@ -28,6 +28,8 @@ struct FilterKernel {
     size_t uniforms_size = 0;          // sizeof(mm_uniforms_<f>) (>= 4)
     std::string row_kernel_name;       // row pre-kernel (empty: none); fills `row_slots` 4-byte arrays of num_rows entries
     int row_slots = 0;
+    int filter_index = -1;             // position in the module's filter list: mm_image::closure_filter of its closures
+    bool closure_fn = false;           // a device function mm_closure_<f> exists (the filter occurs as a closure value)
 };
 
 struct CudaModuleSource {

@@ -75,8 +75,12 @@ struct Userval {
 
 struct FrameData {
     std::vector<unsigned char> uniforms;
+    // image descriptor table of the launch: the kernel's own image uniforms sit at their compile-time slots, images that
+    // only closures reach (their filters read the slot from their uniforms) are appended behind them
     mm_image slots[MM_MAX_IMAGES];
     int nslots = 0;
+    int next_dynamic = 0;
+    std::map<int, int> dynamic_slot_of;  // host image handle -> slot
 };
 
 }  // namespace
@@ -305,7 +309,6 @@ struct Replay {
         case OP_IMAGE_PIXEL_HEIGHT: v.type = T_INT; v.i = inv->images.at(a[0].image).h; return v;
         case OP_RESIZE_IMAGE: {
             HostImage img = inv->images.at(a[0].image);
-            if (img.kind == IMG_CLOSURE) fail("resizing a closure image that is not consumed by a direct call is not supported");
             img.owned = false;
             img.resized = true;
             img.original = a[0].image;
@@ -414,18 +417,61 @@ struct Replay {
     }
 };
 
-// Packs the uniforms a filter's kernel reads and assigns image slots.
-void pack_frame(mmb_invocation *inv, const FilterKernel &k, Replay &rp, FrameData &fd) {
-    fd.uniforms.assign(k.uniforms_size, 0);
-    fd.nslots = 0;
-    memset(fd.slots, 0, sizeof fd.slots);
+void pack_uniform_bytes(mmb_invocation *inv, const FilterKernel &k, Replay &rp, std::vector<unsigned char> &bytes, FrameData &fd, bool fixed_slots,
+                        int depth);
+
+// Device descriptor of a host image.  A closure (filter + argument values) becomes MM_IMAGE_CLOSURE: its filter's frame
+// constants are computed by a host replay with the closure's arguments, like the reference's lazily initialised
+// closure->xy_vars (new_template.c.in:389-398), packed as that filter's uniforms and uploaded; ORIG_VAL on it calls
+// mm_closure_<filter> through mm_closure_dispatch.
+mm_image device_desc(mmb_invocation *inv, FrameData &fd, int image, float t, int depth) {
+    if (image < 0 || image >= (int)inv->images.size()) fail("internal error: bad image handle");
+    if (inv->images[image].kind != IMG_CLOSURE) return to_device_desc(inv->images[image]);
+    if (depth > 16) fail("closure nesting too deep");
+    const HostImage img = inv->images[image];  // copy: the replay below may add images
+    const FilterKernel &fk = inv->backend->source.kernels.at(img.filter);
+    if (!fk.closure_fn) fail("internal error: filter " + img.filter->name + " has no closure entry on the device");
+    const std::vector<HVal> args = img.args;
+    Replay crp(inv, img.filter, args, 0, t, depth + 1);
+    crp.run(crp.code->first);
+    std::vector<unsigned char> blob;
+    pack_uniform_bytes(inv, fk, crp, blob, fd, false, depth + 1);
+    void *d = inv->alloc(std::max<size_t>(blob.size(), 8));
+    ck(cudaMemcpyAsync(d, blob.data(), blob.size(), cudaMemcpyHostToDevice, inv->stream), "cudaMemcpyAsync(closure uniforms)");
+    ck(cudaStreamSynchronize(inv->stream), "sync(closure uniforms)");  // blob is a local
+    mm_image desc;
+    memset(&desc, 0, sizeof desc);
+    desc.kind = MM_IMAGE_CLOSURE;
+    desc.data = d;
+    desc.closure_filter = fk.filter_index;
+    desc.w = img.w; desc.h = img.h; desc.num_frames = 1;
+    desc.xf = img.xf; desc.yf = img.yf;
+    desc.fast_w = desc.fast_h = desc.fast_wm1 = desc.fast_hm1 = desc.fast_nf = -1.0f;
+    return desc;
+}
+
+int dynamic_slot(mmb_invocation *inv, FrameData &fd, int image, float t, int depth) {
+    auto it = fd.dynamic_slot_of.find(image);
+    if (it != fd.dynamic_slot_of.end()) return it->second;
+    if (fd.next_dynamic >= MM_MAX_IMAGES) fail("too many images reachable from one filter (max " + std::to_string(MM_MAX_IMAGES) + ")");
+    const int slot = fd.next_dynamic++;
+    fd.dynamic_slot_of[image] = slot;
+    fd.nslots = std::max(fd.nslots, slot + 1);
+    const mm_image d = device_desc(inv, fd, image, t, depth);  // may allocate further slots
+    fd.slots[slot] = d;
+    return slot;
+}
+
+void pack_uniform_bytes(mmb_invocation *inv, const FilterKernel &k, Replay &rp, std::vector<unsigned char> &bytes, FrameData &fd, bool fixed_slots,
+                        int depth) {
+    bytes.assign(k.uniforms_size, 0);
     for (const UniformField &u : k.uniforms) {
         auto it = rp.env.find(u.value);
         // a frame-constant value defined in the branch of a frame-constant `if` the host did not take
         // is never read by the device either (same branch): leave it zero
         if (it == rp.env.end()) continue;
         const HVal &v = it->second;
-        unsigned char *dst = fd.uniforms.data() + u.offset;
+        unsigned char *dst = bytes.data() + u.offset;
         switch (u.type) {
         case T_INT: case T_NIL: { int x = Replay::as_int(v); memcpy(dst, &x, 4); break; }
         case T_FLOAT: { float x = Replay::as_float(v); memcpy(dst, &x, 4); break; }
@@ -433,19 +479,21 @@ void pack_frame(mmb_invocation *inv, const FilterKernel &k, Replay &rp, FrameDat
         case T_COLOR: memcpy(dst, &v.color, 4); break;
         case T_CURVE: case T_GRADIENT: memcpy(dst, &v.ptr, 8); break;
         case T_IMAGE: {
-            // every image-typed uniform owns the slot the kernel was compiled with (cuda_emit.cpp), so the
-            // generated code indexes P.images with a literal
-            if (v.image < 0 || v.image >= (int)inv->images.size()) fail("internal error: bad image handle");
-            const HostImage &img = inv->images[v.image];
-            if (img.kind == IMG_CLOSURE) fail("a closure image reaches per-pixel code without being called directly; this is not supported");
-            int slot = u.image_slot;
-            if (slot < 0 || slot >= MM_MAX_IMAGES) fail("internal error: image slot out of range");
-            fd.slots[slot] = to_device_desc(img);
-            fd.nslots = std::max(fd.nslots, slot + 1);
+            int slot;
+            if (fixed_slots) {
+                // every image-typed uniform of the launched kernel owns the slot the kernel was compiled with
+                // (cuda_emit.cpp), so the generated code indexes P.images with a literal
+                slot = u.image_slot;
+                if (slot < 0 || slot >= MM_MAX_IMAGES) fail("internal error: image slot out of range");
+                const mm_image d = device_desc(inv, fd, v.image, rp.t, depth);
+                fd.slots[slot] = d;
+                fd.nslots = std::max(fd.nslots, slot + 1);
+            } else
+                slot = dynamic_slot(inv, fd, v.image, rp.t, depth);
             memcpy(dst, &slot, 4);
             break;
         }
-        case T_TUPLE: {
+        case T_TUPLE: case T_TREE_VECTOR: {
             for (int i = 0; i < std::max(1, u.tuple_len); ++i) {
                 float x = i < (int)v.tuple.size() ? v.tuple[i] : 0.f;
                 memcpy(dst + 4 * i, &x, 4);
@@ -457,6 +505,18 @@ void pack_frame(mmb_invocation *inv, const FilterKernel &k, Replay &rp, FrameDat
     }
 }
 
+// Packs the uniforms a filter's kernel reads and fills the image descriptor table of its launches.
+void pack_frame(mmb_invocation *inv, const FilterKernel &k, Replay &rp, FrameData &fd) {
+    fd.nslots = 0;
+    memset(fd.slots, 0, sizeof fd.slots);
+    fd.dynamic_slot_of.clear();
+    int fixed = 0;
+    for (const UniformField &u : k.uniforms) fixed += u.type == T_IMAGE;
+    fd.next_dynamic = fixed;
+    fd.nslots = fixed;
+    pack_uniform_bytes(inv, k, rp, fd.uniforms, fd, true, rp.depth);
+}
+
 struct LaunchGeom {
     int frame_w, frame_h;   // frame_render_width/height the coordinates refer to
     int region_x, region_w;
@@ -465,6 +525,7 @@ struct LaunchGeom {
     int xs_count, ys_count;
     int interleave = 1, phase = 0;  // 8-row block interleaving across ranks (see mm_actual_row)
     int row_limit = -1;
+    const float *xs_dev = nullptr, *ys_dev = nullptr;  // explicit per-column / per-row coordinates instead of CALC_VIRTUAL_X/Y
 };
 
 void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, const LaunchGeom &g, void *out, long long out_stride, int floatmap,
@@ -479,8 +540,8 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     memset(&P, 0, sizeof P);
     P.out = out;
     P.out_stride = out_stride;
-    P.xs = coords(inv, false, g.frame_w, g.off_x, g.xs_count);
-    P.ys = coords(inv, true, g.frame_h, g.off_y, g.ys_count);
+    P.xs = g.xs_dev ? g.xs_dev : coords(inv, false, g.frame_w, g.off_x, g.xs_count);
+    P.ys = g.ys_dev ? g.ys_dev : coords(inv, true, g.frame_h, g.off_y, g.ys_count);
     P.region_x = g.region_x;
     P.region_y = 0;
     P.region_w = g.region_w;
@@ -539,6 +600,20 @@ int Replay::render_image(int idx, int width, int height, bool force) {
         FrameData fd;
         pack_frame(inv, k, sub, fd);
         LaunchGeom g{width, height, 0, width, 0, height, 0.f, 0.f, width, height};
+        if (src.resized) {
+            // A resize wrapper around the closure (the caller's pixel-size factors): the reference then does not run the
+            // closure's calc_lines but samples it pixel by pixel through ORIG_VAL at fx = ((float)x - bx) / ax scaled by
+            // the factors (builtins.c:303-342, opmacros.h:203-207).  Same kernel, those coordinates instead of
+            // CALC_VIRTUAL_X/Y.
+            std::vector<float> c((size_t)width + height);
+            for (int x = 0; x < width; ++x) c[x] = (((float)x - out.bx) / out.ax) * src.xf;
+            for (int y = 0; y < height; ++y) c[(size_t)width + y] = (((float)y - out.by) / out.ay) * src.yf;
+            float *d = (float *)inv->alloc(sizeof(float) * c.size());
+            ck(cudaMemcpyAsync(d, c.data(), sizeof(float) * c.size(), cudaMemcpyHostToDevice, inv->stream), "cudaMemcpyAsync(coords)");
+            ck(cudaStreamSynchronize(inv->stream), "sync(coords)");
+            g.xs_dev = d;
+            g.ys_dev = d + width;
+        }
         launch_filter(inv, src.filter, fd, g, out.data, (long long)sizeof(float) * 4 * width, 1, 0, 0.0f);
     } else if (src.kind == IMG_FLOATMAP) {
         // forced re-render of a floatmap: nearest lookup through get_floatmap_pixel (builtins.c:303-342)

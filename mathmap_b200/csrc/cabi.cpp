@@ -45,6 +45,33 @@ mmb_module *mmb_compile(const char *source) {
     return m.release();
 }
 
+char *mmb_design_to_source(const char *design_text, const char *filter_search_path) {
+    if (!design_text || !filter_search_path) { g_last_error = "mmb_design_to_source: null argument"; return nullptr; }
+    try {
+        std::string src = mm::design_to_source(design_text, filter_search_path);
+        char *out = (char *)malloc(src.size() + 1);
+        if (!out) { g_last_error = "out of memory"; return nullptr; }
+        memcpy(out, src.c_str(), src.size() + 1);
+        return out;
+    } catch (mm::CompileError &e) {
+        g_last_error = e.message;
+        return nullptr;
+    } catch (std::exception &e) {
+        g_last_error = std::string("internal error: ") + e.what();
+        return nullptr;
+    }
+}
+
+void mmb_free_string(char *s) { free(s); }
+
+mmb_module *mmb_compile_design(const char *design_text, const char *filter_search_path) {
+    char *src = mmb_design_to_source(design_text, filter_search_path);
+    if (!src) return nullptr;
+    mmb_module *m = mmb_compile(src);
+    free(src);
+    return m;
+}
+
 mmb_module *mmb_load_ir(const char *ir_text) {
     if (!ir_text) { g_last_error = "mmb_load_ir: null text"; return nullptr; }
     try {

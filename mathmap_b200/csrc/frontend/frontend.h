@@ -92,5 +92,8 @@ void register_all_builtins(Module &m);  // builtins.cpp
 void register_native_filters(Module &m);
 // Parses `source` into `m` (filters, main filter).  Throws CompileError.
 void parse_module(Module &m, const std::string &source);
+// A composition (".mmc" design text) -> MathMap source; node types are looked up by main-filter name among the
+// .mm / .mmc files under `filter_search_path` (design.cpp).  Throws CompileError.
+std::string design_to_source(const std::string &design_text, const std::string &filter_search_path);
 
 }  // namespace mm

@@ -614,12 +614,16 @@ MM_DEV mm_tup<4> mm_floatmap_pixel(const mm_image &img, float x, float y) {
     return t;
 }
 
-// ORIG_VAL (opmacros.h:199-216); closures never reach here (inlined or called directly)
+// defined at the end of every generated module (backend/cuda_emit.cpp)
+__device__ mm_tup<4> mm_closure_dispatch(const mm_params &P, const mm_image &img, float x, float y, float t);
+
+// ORIG_VAL (opmacros.h:199-216); closures known at compile time are inlined or called directly, the others dispatch
 MM_DEV mm_tup<4> mm_orig_val(const mm_params &P, int image, float x, float y, float t) {
     const mm_image &img = P.images[image];
     x = __fmul_rn(x, img.xf);  // 1.0 unless a RESIZE wrapper survived to run time
     y = __fmul_rn(y, img.yf);
     if (img.kind == MM_IMAGE_FLOATMAP) return mm_floatmap_pixel(img, x, y);
+    if (img.kind == MM_IMAGE_CLOSURE) return mm_closure_dispatch(P, img, x, y, t);  // img->v.closure.func, opmacros.h:208
     mm_tup<4> r;
 #if MM_AA
     if (mm_bilinear_interior(P, img, x, y, t, r)) return r;

@@ -1,12 +1,12 @@
 // Plain structs shared by host code and device code (NVRTC and nvcc).
 #pragma once
 
-#define MM_MAX_IMAGES 24
+#define MM_MAX_IMAGES 32
 #define MM_CURVE_POINTS 1024
 
 typedef unsigned int mm_color;
 
-enum { MM_IMAGE_DRAWABLE = 0, MM_IMAGE_FLOATMAP = 1 };
+enum { MM_IMAGE_DRAWABLE = 0, MM_IMAGE_FLOATMAP = 1, MM_IMAGE_CLOSURE = 2 };
 
 // One input or intermediate image.  Drawables are RGBA8 (R first); floatmaps are
 // float4 per pixel (reference drawable.h:92-125, floatmap.c:30-47).
@@ -21,7 +21,7 @@ struct mm_image {
     // Bounds of the samplers' interior fast paths as floats, filled by the host: w, h, w-1, h-1 and num_frames
     // when w, h < 2^22 and the image is a drawable, else all -1 (the fast-path tests then never hold).
     float fast_w, fast_h, fast_wm1, fast_hm1, fast_nf;
-    int pad0;
+    int closure_filter;    // MM_IMAGE_CLOSURE: which filter; `data` then points at that filter's packed uniforms (device memory)
 };
 
 // Per-launch parameters (the invocation / frame / slice fields calc_lines reads,

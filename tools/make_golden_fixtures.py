@@ -43,7 +43,7 @@ for line in open(os.path.join(REF, "run_tests.sh")):
 # every example filter: the reference's test list has golden pictures for 80 of them, the parity tests render the
 # rest too (CUDA path against the oracle)
 import glob
-for src in sorted(glob.glob("/root/reference/examples/**/*.mm", recursive=True)):
+for src in sorted(glob.glob("/root/reference/examples/**/*.mm", recursive=True) + glob.glob("/root/reference/examples/**/*.mmc", recursive=True)):
     rel = os.path.relpath(src, "/root/reference")
     dst = os.path.join(OUT, "filters", rel)
     os.makedirs(os.path.dirname(dst), exist_ok=True)
