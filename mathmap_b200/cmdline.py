@@ -47,6 +47,7 @@ def main(argv=None):
     ap.add_argument("--bench-no-backend", action="store_true")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--fast-math", action="store_true")
+    ap.add_argument("--filter-path", default=None, help="directory tree searched for the node types of a .mmc composition")
     ap.add_argument("--version", action="store_true")
     ap.add_argument("rest", nargs="*")
     a = ap.parse_args(argv)
@@ -63,7 +64,10 @@ def main(argv=None):
         source, outfile = a.rest
     t0 = time.perf_counter()
     try:
-        module = mb.Module(source=source)
+        if a.script_file and a.script_file.endswith(".mmc"):  # a composition (not on the reference's command line; GIMP-side there)
+            module = mb.Module.from_file(a.script_file, filter_path=a.filter_path)
+        else:
+            module = mb.Module(source=source)
     except mb.MathMapError as e:
         print("Error: %s" % e, file=sys.stderr)
         return 1
