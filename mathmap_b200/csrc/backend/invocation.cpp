@@ -681,6 +681,40 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
     snprintf(key, sizeof key, "gauss:%d:%a:%a", in, (double)h, (double)v);
     auto it = inv->native_cache.find(key);
     if (it != inv->native_cache.end()) return it->second;
+    // A drawable input whose blur takes the IIR path is not rendered to a floatmap first: every channel of that
+    // floatmap would be k/255 of a byte, so the column pass reads RGBA8 (the drawable itself when render_image is the
+    // identity on texels, else a resampled RGBA8 copy) and converts on load; results are the same floats.
+    const HostImage in_img = inv->images.at(in);
+    if (in_img.kind == IMG_DRAWABLE) {
+        const int w = inv->W, hgt = inv->H;
+        const float ax = (float)((float)(w - 1) / 2.0), ay = (float)((float)(hgt - 1) / 2.0) * -1.0f;  // floatmap_alloc, floatmap.c:30-47
+        const float bx = ax, by = (float)((float)(hgt - 1) / 2.0);
+        const float sh = (float)fabs((double)(h * ax)), sv = (float)fabs((double)(v * ay));
+        if (!(sh < 0.5f || sv < 0.5f)) {
+            HostImage out;
+            out.kind = IMG_FLOATMAP;
+            out.w = w;
+            out.h = hgt;
+            out.ax = ax; out.bx = bx; out.ay = ay; out.by = by;
+            out.data = inv->alloc(sizeof(float) * 4 * (size_t)w * hgt);
+            mm_image d = to_device_desc(in_img);
+            const void *bytes_in = in_img.data;
+            if (!drawable_render_is_identity(d, w, hgt, ax, bx, ay, by, inv->cfg.supersampling)) {
+                void *resampled = inv->alloc((size_t)w * hgt * 4);
+                launch_drawable_to_bytes(d, resampled, w, hgt, ax, bx, ay, by, inv->cfg.edge_x, inv->cfg.edge_y, inv->edge_color_x, inv->edge_color_y,
+                                         inv->cfg.supersampling, inv->stream);
+                inv->launches++;
+                bytes_in = resampled;
+            }
+            void *scratch = inv->alloc(gauss_iir_scratch_bytes(w, hgt));
+            launch_gauss_iir(bytes_in, true, (float *)out.data, (double *)scratch, w, hgt, sh, sv, inv->stream);
+            inv->launches += 2;
+            ck(cudaGetLastError(), "gaussian blur launch");
+            int idx = add_image(out);
+            inv->native_cache[key] = idx;
+            return idx;
+        }
+    }
     int fm = in;
     if (inv->images.at(in).kind != IMG_FLOATMAP) fm = render_image(in, inv->W, inv->H);
     HostImage src = inv->images.at(fm);
@@ -696,7 +730,7 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
         inv->launches += 2;
     } else {
         void *scratch = inv->alloc(gauss_iir_scratch_bytes(src.w, src.h));
-        launch_gauss_iir((const float *)src.data, (float *)out.data, (double *)scratch, src.w, src.h, sh, sv, inv->stream);
+        launch_gauss_iir(src.data, false, (float *)out.data, (double *)scratch, src.w, src.h, sh, sv, inv->stream);
         inv->launches += 2;
     }
     ck(cudaGetLastError(), "gaussian blur launch");
@@ -1165,7 +1199,7 @@ int mmb_gaussian_blur_device(int device, const float *device_in, float *device_o
         } else {
             void *scratch = nullptr;
             ck(cudaMalloc(&scratch, gauss_iir_scratch_bytes(width, height)), "cudaMalloc(scratch)");
-            launch_gauss_iir(device_in, device_out, (double *)scratch, width, height, sigma_h_px, sigma_v_px, s);
+            launch_gauss_iir(device_in, false, device_out, (double *)scratch, width, height, sigma_h_px, sigma_v_px, s);
             cudaStreamSynchronize(s);
             cudaFree(scratch);
         }

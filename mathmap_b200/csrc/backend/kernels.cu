@@ -37,6 +37,62 @@ __global__ void __launch_bounds__(256) drawable_to_floatmap_kernel(mm_image img,
     out[(size_t)y * width + x] = make_float4(mm_red(c), mm_green(c), mm_blue(c), mm_alpha(c));
 }
 
+// The same lookup, but the result stays RGBA8 in memory order (R first): every channel of render_image's floatmap is
+// k/255 of such a byte, so a consumer that converts on load (the blur's column pass) reads a quarter of the bytes.
+template <int EX, int EY>
+__global__ void __launch_bounds__(256) drawable_to_bytes_kernel(mm_image img, unsigned *out, int width, int height, float ax, float bx, float ay, float by,
+                                                                mm_color edge_x, mm_color edge_y, int supersampling) {
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= width || y >= height) return;
+    float fx = __fdiv_rn(__fsub_rn((float)x, bx), ax), fy = __fdiv_rn(__fsub_rn((float)y, by), ay);
+    fx = __fmul_rn(fx, img.xf);
+    fy = __fmul_rn(fy, img.yf);
+    float px = __fmul_rn(__fadd_rn(fx, img.mx), img.sx), py = -__fmul_rn(__fsub_rn(fy, img.my), img.sy);
+    if (!supersampling) { px = __fadd_rn(px, 0.5f); py = __fadd_rn(py, 0.5f); }
+    int ix = mm_f2i(floorf(px)), iy = mm_f2i(floorf(py));
+    mm_apply_edge_behaviour<EX, EY>(ix, iy, img.w, img.h);
+    unsigned word;  // memory order
+    if (ix < 0 || ix >= img.w) word = __byte_perm(edge_x, 0, 0x0123);
+    else if (iy < 0 || iy >= img.h) word = __byte_perm(edge_y, 0, 0x0123);
+    else word = __ldg((const unsigned *)img.data + ((size_t)iy * img.w + ix));
+    out[(size_t)y * width + x] = word;
+}
+
+void launch_drawable_to_bytes(const mm_image &img, void *out, int width, int height, float ax, float bx, float ay, float by, int edge_x_mode,
+                              int edge_y_mode, unsigned edge_x, unsigned edge_y, int supersampling, cudaStream_t stream) {
+    dim3 grid((width + 31) / 32, (height + 7) / 8);
+#define MM_CASE(EX, EY) \
+    if (edge_x_mode == EX && edge_y_mode == EY) drawable_to_bytes_kernel<EX, EY><<<grid, 256, 0, stream>>>(img, (unsigned *)out, width, height, ax, bx, ay, by, edge_x, edge_y, supersampling);
+    MM_CASE(0, 0) MM_CASE(0, 1) MM_CASE(0, 2) MM_CASE(0, 3)
+    MM_CASE(1, 0) MM_CASE(1, 1) MM_CASE(1, 2) MM_CASE(1, 3)
+    MM_CASE(2, 0) MM_CASE(2, 1) MM_CASE(2, 2) MM_CASE(2, 3)
+    MM_CASE(3, 0) MM_CASE(3, 1) MM_CASE(3, 2) MM_CASE(3, 3)
+#undef MM_CASE
+}
+
+// Is render_image of this drawable at width x height the identity on texels (output pixel (x, y) = texel (x, y), no
+// edge pixel)?  Decided with the kernel's own float arithmetic, evaluated on the host for every column and row.
+bool drawable_render_is_identity(const mm_image &img, int width, int height, float ax, float bx, float ay, float by, int supersampling) {
+    if (img.w != width || img.h != height) return false;
+    auto f2i = [](float f) { return (!(f > -2147483904.0f && f < 2147483648.0f)) ? (int)0x80000000 : (int)f; };
+    for (int x = 0; x < width; ++x) {
+        volatile float fx = ((float)x - bx) / ax;
+        fx = fx * img.xf;
+        volatile float px = (fx + img.mx) * img.sx;
+        if (!supersampling) px = px + 0.5f;
+        if (f2i(floorf(px)) != x) return false;
+    }
+    for (int y = 0; y < height; ++y) {
+        volatile float fy = ((float)y - by) / ay;
+        fy = fy * img.yf;
+        volatile float t = (fy - img.my) * img.sy;
+        volatile float py = -t;
+        if (!supersampling) py = py + 0.5f;
+        if (f2i(floorf(py)) != y) return false;
+    }
+    return true;
+}
+
 void launch_drawable_to_floatmap(const mm_image &img, float *out, int width, int height, float ax, float bx, float ay, float by, int edge_x_mode,
                                  int edge_y_mode, unsigned edge_x, unsigned edge_y, int supersampling, cudaStream_t stream) {
     dim3 grid((width + 31) / 32, (height + 7) / 8);
@@ -123,10 +179,14 @@ __device__ __forceinline__ void iir_shift(IirState &st, double s0, double acc) {
 // the recursion instead of stalling every step.
 #define IIR_T 8
 
+// A line's samples are floats, or (column pass straight from an RGBA8 picture) bytes converted like render_image does
+__device__ __forceinline__ float iir_sample(const float *p) { return *p; }
+__device__ __forceinline__ float iir_sample(const unsigned char *p) { return mm_unit_from_byte(*p); }
+
 // one step without prefetch: the boundary steps and the tail that does not fill a tile
-template <bool COMBINE>
-__device__ __forceinline__ void iir_single(IirState &st, const IirCoeffs &c, const float *pp, float *oo, double *ss, int t, double initial) {
-    const double s0 = (double)*pp;
+template <bool COMBINE, class S>
+__device__ __forceinline__ void iir_single(IirState &st, const IirCoeffs &c, const S *pp, float *oo, double *ss, int t, double initial) {
+    const double s0 = (double)iir_sample(pp);
     const double acc = t < 4 ? iir_step_boundary(c, s0, st, t, initial) : iir_step_steady(c, s0, st);
     if (COMBINE) *oo = (float)__dadd_rn(acc, *ss);
     else *ss = acc;
@@ -135,8 +195,8 @@ __device__ __forceinline__ void iir_single(IirState &st, const IirCoeffs &c, con
 
 // steps t0 .. t1-1 of one sweep; pp/oo/ss point at the sample of step t0, de/ds
 // are the signed strides (floats / doubles) from one step to the next
-template <bool COMBINE>
-__device__ __forceinline__ void iir_run(IirState &st, const IirCoeffs &c, const float *pp, float *oo, double *ss, long long de, long long ds, int t0, int t1,
+template <bool COMBINE, class S>
+__device__ __forceinline__ void iir_run(IirState &st, const IirCoeffs &c, const S *pp, float *oo, double *ss, long long de, long long ds, int t0, int t1,
                                         double initial) {
     int t = t0;
 #pragma unroll 1
@@ -147,7 +207,7 @@ __device__ __forceinline__ void iir_run(IirState &st, const IirCoeffs &c, const 
         double curv[IIR_T], nxtv[IIR_T];
 #pragma unroll
         for (int i = 0; i < IIR_T; ++i) {
-            nxt[i] = pp[i * de];
+            nxt[i] = iir_sample(pp + i * de);
             if (COMBINE) nxtv[i] = ss[i * ds];
         }
 #pragma unroll 1
@@ -157,7 +217,7 @@ __device__ __forceinline__ void iir_run(IirState &st, const IirCoeffs &c, const 
             if (tile + 1 < ntiles) {
 #pragma unroll
                 for (int i = 0; i < IIR_T; ++i) {
-                    nxt[i] = pp[(IIR_T + i) * de];
+                    nxt[i] = iir_sample(pp + (IIR_T + i) * de);
                     if (COMBINE) nxtv[i] = ss[(IIR_T + i) * ds];
                 }
             }
@@ -181,7 +241,8 @@ __device__ __forceinline__ void iir_run(IirState &st, const IirCoeffs &c, const 
 // the same IIR_PAIRS (line, channel) recursions; the sweep direction is uniform
 // per warp, the hand-over between the phases is one __syncthreads().
 #define IIR_PAIRS 32
-__global__ void __launch_bounds__(2 * IIR_PAIRS) gauss_iir_lines_kernel(const float *in, float *out, double *scratch, int nlines, int n, long long line_stride,
+template <class S>
+__global__ void __launch_bounds__(2 * IIR_PAIRS) gauss_iir_lines_kernel(const S *in, float *out, double *scratch, int nlines, int n, long long line_stride,
                                                                          long long elem_stride, long long scratch_line_stride,
                                                                          long long scratch_elem_stride, GaussCoeffs C) {
     const int anti = threadIdx.x >= IIR_PAIRS;
@@ -193,7 +254,7 @@ __global__ void __launch_bounds__(2 * IIR_PAIRS) gauss_iir_lines_kernel(const fl
     const int len1 = anti ? nn - h : h;
     const int k0 = anti ? nn - 1 : 0;
     const long long de = anti ? -elem_stride : elem_stride, ds = anti ? -scratch_elem_stride : scratch_elem_stride;
-    const float *p = in + (size_t)line * line_stride + ch + (long long)k0 * elem_stride;
+    const S *p = in + (size_t)line * line_stride + ch + (long long)k0 * elem_stride;
     float *o = out + (size_t)line * line_stride + ch + (long long)k0 * elem_stride;
     double *sc = scratch + (size_t)line * scratch_line_stride + ch + (long long)k0 * scratch_elem_stride;
     IirCoeffs c;
@@ -205,7 +266,7 @@ __global__ void __launch_bounds__(2 * IIR_PAIRS) gauss_iir_lines_kernel(const fl
     }
     IirState st = {0, 0, 0, 0, 0, 0, 0, 0};
     double initial = 0.0;
-    if (nn > 0) initial = (double)*p;
+    if (nn > 0) initial = (double)iir_sample(p);
     iir_run<false>(st, c, p, o, sc, de, ds, 0, len1, initial);
     __syncthreads();
     iir_run<true>(st, c, p + len1 * de, o + len1 * de, sc + len1 * ds, de, ds, len1, nn, initial);
@@ -245,20 +306,28 @@ void gauss_iir_constants_host(float std_dev, double *out30) {
 
 size_t gauss_iir_scratch_bytes(int width, int height) { return sizeof(double) * 4 * (size_t)width * height; }
 
-// in -> out (float4 [height][width]; may alias); scratch: gauss_iir_scratch_bytes()
-void launch_gauss_iir(const float *in, float *out, double *scratch, int width, int height, float sigma_h, float sigma_v, cudaStream_t stream) {
+// in -> out (float4 [height][width]; may alias); scratch: gauss_iir_scratch_bytes().  With in_is_rgba8 the input is
+// uchar4 [height][width] whose bytes stand for k/255 (never aliases out).
+void launch_gauss_iir(const void *in, bool in_is_rgba8, float *out, double *scratch, int width, int height, float sigma_h, float sigma_v,
+                      cudaStream_t stream) {
     GaussCoeffs c;
-    // vertical pass: lines are columns
+    // vertical pass: lines are columns (in and out have the same element strides: 4 channels per pixel)
     find_iir_constants(c, sigma_v);
     {
         int threads = width * 4;
-        gauss_iir_lines_kernel<<<(threads + IIR_PAIRS - 1) / IIR_PAIRS, 2 * IIR_PAIRS, 0, stream>>>(in, out, scratch, width, height, 4, (long long)width * 4, 4, (long long)width * 4, c);
+        if (in_is_rgba8)
+            gauss_iir_lines_kernel<unsigned char><<<(threads + IIR_PAIRS - 1) / IIR_PAIRS, 2 * IIR_PAIRS, 0, stream>>>(
+                (const unsigned char *)in, out, scratch, width, height, 4, (long long)width * 4, 4, (long long)width * 4, c);
+        else
+            gauss_iir_lines_kernel<float><<<(threads + IIR_PAIRS - 1) / IIR_PAIRS, 2 * IIR_PAIRS, 0, stream>>>(
+                (const float *)in, out, scratch, width, height, 4, (long long)width * 4, 4, (long long)width * 4, c);
     }
     // horizontal pass: lines are rows, in place on `out`
     find_iir_constants(c, sigma_h);
     {
         int threads = height * 4;
-        gauss_iir_lines_kernel<<<(threads + IIR_PAIRS - 1) / IIR_PAIRS, 2 * IIR_PAIRS, 0, stream>>>(out, out, scratch, height, width, (long long)width * 4, 4, (long long)width * 4, 4, c);
+        gauss_iir_lines_kernel<float><<<(threads + IIR_PAIRS - 1) / IIR_PAIRS, 2 * IIR_PAIRS, 0, stream>>>(out, out, scratch, height, width, (long long)width * 4, 4,
+                                                                                                        (long long)width * 4, 4, c);
     }
 }
 

@@ -12,7 +12,11 @@ namespace mmbackend {
 void launch_drawable_to_floatmap(const mm_image &img, float *out, int width, int height, float ax, float bx, float ay, float by, int edge_x_mode,
                                  int edge_y_mode, unsigned edge_x, unsigned edge_y, int supersampling, cudaStream_t stream);
 size_t gauss_iir_scratch_bytes(int width, int height);
-void launch_gauss_iir(const float *in, float *out, double *scratch, int width, int height, float sigma_h, float sigma_v, cudaStream_t stream);
+void launch_drawable_to_bytes(const mm_image &img, void *out, int width, int height, float ax, float bx, float ay, float by, int edge_x_mode,
+                              int edge_y_mode, unsigned edge_x, unsigned edge_y, int supersampling, cudaStream_t stream);
+bool drawable_render_is_identity(const mm_image &img, int width, int height, float ax, float bx, float ay, float by, int supersampling);
+void launch_gauss_iir(const void *in, bool in_is_rgba8, float *out, double *scratch, int width, int height, float sigma_h, float sigma_v,
+                      cudaStream_t stream);
 bool launch_gauss_rle(const float *in, float *tmp, float *out, int width, int height, float sigma_h, float sigma_v, cudaStream_t stream);
 void gauss_iir_constants_host(float std_dev, double *out30);
 void launch_supersample_combine(const unsigned char *shortimg, const unsigned char *longimg, unsigned char *out, int width, int height, int long_rows,

@@ -145,6 +145,17 @@ def test_gaussian_blur_iir_matches_oracle():
         want = OracleFilter(m.ir).render(384, 256, {"in": img, "dev": dev}, antialiasing=True)
         exact, le1, mx = compare_u8(got, want)
         assert exact >= 99.99, "dev=%g: %.4f %% exact, max %d" % (dev, exact, mx)
+    # input of another size than the render (and supersampling, which shifts the lookup): the column pass then reads a
+    # resampled RGBA8 copy instead of the drawable itself
+    small = synthetic_rgba(200, 150)
+    for ss in (False, True):
+        inv = mb.Invocation(m, 384, 256, antialiasing=True, supersampling=ss)
+        inv.set("in", small)
+        inv.set("dev", 0.05)
+        got = inv.render(0, 0.0)
+        want = OracleFilter(m.ir).render(384, 256, {"in": small, "dev": 0.05}, antialiasing=True, supersampling=ss)
+        exact, le1, mx = compare_u8(got, want)
+        assert exact >= 99.99, "resampled input, supersampling=%s: %.4f %% exact, max %d" % (ss, exact, mx)
 
 
 def test_output_bpp_variants():
