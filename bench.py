@@ -46,7 +46,8 @@ WORKLOADS = {
 # --fmad=false is required for bit parity.  SURVEY.md section 8d counts 45 (with the NEGs); 39 is the instruction-level figure.
 MANDELBROT_FLOPS_PER_ITERATION = 39
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full captures, profiles/r01_*_ncu_full.txt
-NCU_TRAFFIC_BYTES = {"mandelbrot": 6.96e6 + 1.0171e9, "twirl": 241.8e6 + 229.4e6, "droste": 212.1e6 + 224.0e6}
+# (gauss: the dominant kernel of its four launches, the row pass of the IIR)
+NCU_TRAFFIC_BYTES = {"mandelbrot": 6.96e6 + 1.0171e9, "twirl": 241.8e6 + 229.4e6, "droste": 212.1e6 + 224.0e6, "gauss": 4.238e9 + 3.194e9}
 B200_SMS, FP32_LANES_PER_SM = 148, 128
 
 

@@ -1,7 +1,7 @@
 """Debug aid: renders a filter truncated after each top-level statement on the GPU and with the oracle and reports where they
-first diverge.  Usage: python tools/debug_stages.py FILTER.mm VAR [WIDTH HEIGHT]  (VAR: a 2-tuple variable to visualise)"""
+first diverge.  Usage: python tests/tools/debug_stages.py FILTER.mm VAR [WIDTH HEIGHT]  (VAR: a 2-tuple variable to visualise)"""
 import os, re, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import mathmap_b200 as mb

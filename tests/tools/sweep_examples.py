@@ -1,7 +1,7 @@
 """Renders every example filter under a directory on the GPU and with the oracle (default uservals, synthetic image inputs)
-and reports the agreement.  Usage: python tools/sweep_examples.py DIR [SIZE] > report.txt"""
+and reports the agreement.  Usage: python tests/tools/sweep_examples.py DIR [SIZE] > report.txt"""
 import glob, os, sys, time, traceback
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import mathmap_b200 as mb
