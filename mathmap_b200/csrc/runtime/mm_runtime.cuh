@@ -62,6 +62,7 @@ MM_DEV void mm_pixel_coords(int &col, int &row) {
 }
 #include "mm_types.h"
 #include "mm_elliptic.h"
+#include "mm_glibc_float.h"
 
 template <int N> struct mm_tup { float v[N]; };
 
@@ -238,14 +239,15 @@ MM_DEV float2 mm_cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y *
 // The reference calls glibc's FLOAT complex functions (ops.lisp:196-213: csqrtf, csinf, ..., cpowf).  Those work in
 // float arithmetic on top of the float libm primitives, so the functions below follow glibc's formulas
 // (math/s_c*_template.c) step by step in float, with each primitive (sinf, coshf, logf, hypotf, atan2f ...) evaluated in
-// double and narrowed, i.e. correctly rounded.  glibc's own primitives are correctly rounded for 74 % (sinhf) to 100 %
-// (hypotf, sqrtf) of arguments, so results agree with the host's to the bit in most cases and to 1 ulp otherwise.
+// double and narrowed, i.e. correctly rounded, except sinhf, coshf, atan2f and log1pf, which glibc does not round
+// correctly and which are therefore glibc's own algorithms restated bit for bit (mm_glibc_float.h).  What is left to
+// differ are glibc's sinf/cosf (98.7 % correctly rounded), expf and logf (99.9 %).
 // Arguments beyond glibc's overflow guards (|x| > 44 or 88) and non-finite ones take the plain double formula.
 #define MM_FLT_MIN 1.17549435e-38f
 #define MM_FLT_EPSILON 1.19209290e-07f
 MM_DEV bool mm_c_finite(float2 z) { return isfinite(z.x) && isfinite(z.y); }
-MM_DEV float mm_cr_sinh(float x) { return (float)sinh((double)x); }
-MM_DEV float mm_cr_cosh(float x) { return (float)cosh((double)x); }
+MM_DEV float mm_cr_sinh(float x) { return mm_g_sinhf(x); }  // glibc's sinhf / coshf bit for bit (mm_glibc_float.h)
+MM_DEV float mm_cr_cosh(float x) { return mm_g_coshf(x); }
 MM_DEV void mm_cr_sincos(float x, float &s, float &c) {  // glibc: sincosf unless |x| <= FLT_MIN
     if (fabsf(x) > MM_FLT_MIN) { double ds, dc; sincos((double)x, &ds, &dc); s = (float)ds; c = (float)dc; }
     else { s = x; c = 1.0f; }
@@ -286,23 +288,23 @@ MM_DEV float2 mm_clog(float2 z) {
         return mm_c_narrow(mm_cd_log(mm_cd_of(z)));
     if (ax < ay) { const float t = ax; ax = ay; ay = t; }
     float re;
-    if (ax == 1.0f) re = __fmul_rn((float)log1p((double)__fmul_rn(ay, ay)), 0.5f);
+    if (ax == 1.0f) re = __fmul_rn(mm_g_log1pf(__fmul_rn(ay, ay)), 0.5f);
     else if (ax > 1.0f && ax < 2.0f && ay < 1.0f) {
         float d2m1 = __fmul_rn(__fsub_rn(ax, 1.0f), __fadd_rn(ax, 1.0f));
         if (ay >= MM_FLT_EPSILON) d2m1 = __fadd_rn(d2m1, __fmul_rn(ay, ay));
-        re = __fmul_rn((float)log1p((double)d2m1), 0.5f);
+        re = __fmul_rn(mm_g_log1pf(d2m1), 0.5f);
     } else if (ax < 1.0f && ax >= 0.5f && ay < MM_FLT_EPSILON / 2.0f) {
         const float d2m1 = __fmul_rn(__fsub_rn(ax, 1.0f), __fadd_rn(ax, 1.0f));
-        re = __fmul_rn((float)log1p((double)d2m1), 0.5f);
+        re = __fmul_rn(mm_g_log1pf(d2m1), 0.5f);
     } else if (ax < 1.0f && ax >= 0.5f && __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)) >= 0.5f) {
         // __x2y2m1f: x^2 + y^2 - 1 evaluated exactly, rounded once (exact in double for float inputs)
         const double d = __dsub_rn(__dadd_rn(__dmul_rn((double)ax, (double)ax), __dmul_rn((double)ay, (double)ay)), 1.0);
-        re = __fmul_rn((float)log1p((double)(float)d), 0.5f);
+        re = __fmul_rn(mm_g_log1pf((float)d), 0.5f);
     } else
         re = (float)log((double)mm_hypot(ax, ay));
-    return make_float2(re, (float)atan2((double)z.y, (double)z.x));
+    return make_float2(re, mm_g_atan2f(z.y, z.x));
 }
-MM_DEV float mm_carg(float2 z) { return mm_atan2(z.y, z.x); }
+MM_DEV float mm_carg(float2 z) { return mm_g_atan2f(z.y, z.x); }  // cargf = atan2f, ops.lisp:205
 MM_DEV float2 mm_cpow(float2 a, float2 b) {
     // glibc cpowf(x, c) = cexpf(c * clogf(x)) in float complex arithmetic
     float2 l = mm_clog(a);
