@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--fast-math", action="store_true", help="CUDA float libm instead of double-evaluated libm (parity mode is the default)")
     ap.add_argument("--warp-width", type=int, default=None)
+    ap.add_argument("--rows", type=int, default=None, help="32x8 tiles one block renders in sequence (mmb_set_rows_per_thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -206,7 +207,7 @@ def main():
 
     script, W, H, uv, aa, frames, desc = WORKLOADS[args.workload]
     m = mb.Module.from_file(os.path.join(FILTERS, script))
-    inv = mb.Invocation(m, W, H, device=local_rank, antialiasing=aa, precise=not args.fast_math, warp_width=args.warp_width)
+    inv = mb.Invocation(m, W, H, device=local_rank, antialiasing=aa, precise=not args.fast_math, warp_width=args.warp_width, rows_per_thread=args.rows)
     for k, v in uv.items():
         inv.set(k, v)
     h2d_bytes = 0

@@ -378,11 +378,34 @@ struct Emitter {
         out << ind << "}\n";
     }
 
+    // "Direct output": the filter's last two statements are  v = ORIG_VAL(...); OUTPUT_TUPLE(v)  with no other use
+    // of v, i.e. the pixel IS a sample (every distortion filter).  The sampler's interior fast path may then hand
+    // over the RGBA8 word it has already rounded instead of four floats that the store would quantise again
+    // (k/255 narrowed to float, times 255, truncated, is k for every byte k).
+    const Stmt *direct_sample = nullptr, *direct_output = nullptr;
+    void find_direct_output(const Stmt *first) {
+        const Stmt *prev = nullptr, *last = nullptr;
+        for (const Stmt *s = first; s; s = s->next) { prev = last; last = s; }
+        if (!prev || prev->kind != ST_ASSIGN || last->kind != ST_ASSIGN) return;
+        if (last->rhs->kind != RHS_OP || last->rhs->op->id != OP_OUTPUT_TUPLE || prev->rhs->kind != RHS_OP || prev->rhs->op->id != OP_ORIG_VAL) return;
+        const Primary &a = last->rhs->args[0];
+        if (a.is_const || a.value != prev->lhs || prev->lhs->uses.size() != 1) return;
+        if (!on_device(prev->lhs->level) || !on_device(last->lhs->level)) return;
+        direct_sample = prev;
+        direct_output = last;
+    }
+
     void emit_stmts(const Stmt *s, const std::string &ind) {
         for (; s; s = s->next) {
             switch (s->kind) {
             case ST_ASSIGN:
                 if (!on_device(s->lhs->level) || fused.count(s)) break;
+                if (s == direct_sample) {
+                    const Rhs *r = s->rhs;
+                    out << ind << vname(s->lhs) << " = mm_orig_val_out(P, " << prim(r->args[2]) << ", " << as_float(r->args[0]) << ", "
+                        << as_float(r->args[1]) << ", " << as_float(r->args[3]) << ", mm_word, mm_have_word);\n";
+                    break;
+                }
                 // sin(v) and cos(v) of the same value in one block share one range reduction
                 if (s->rhs->kind == RHS_OP && (s->rhs->op->id == OP_SIN || s->rhs->op->id == OP_COS) && s->lhs->cv->type == T_FLOAT) {
                     const int other = s->rhs->op->id == OP_SIN ? OP_COS : OP_SIN;
@@ -512,6 +535,7 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         // body first (discovers uniforms and row exports)
         std::vector<const Value *> decls;
         e.collect_decls(code->first, decls);
+        e.find_direct_output(code->first);
         e.emit_stmts(code->first, "    ");
         std::string body = e.out.str();
         Emitter er(m, *code, Emitter::ROW, called);
@@ -629,21 +653,27 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         }
         fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H) " << k.kernel_name << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
            << name << " U, const __grid_constant__ mm_rowvals_" << name << " RV) {\n"
-           << "    int col, row;\n"
-           << "    mm_pixel_coords(col, row);\n"
-           << "    if (col >= P.region_w || row >= P.num_rows) return;\n"
+           << "    int col, mm_row0;\n"
+           << "    mm_pixel_coords(col, mm_row0);\n"
+           << "    if (col >= P.region_w) return;\n"
            << "    const float x = __ldg(P.xs + (col + P.region_x));\n"
+           << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)x;\n"
+           << "#pragma unroll 1\n"
+           << "    for (int mm_rep = 0; mm_rep < MM_ROWS; ++mm_rep) {\n"
+           << "    const int row = mm_row0 + mm_rep * MM_BLOCK_H;\n"
+           << "    if (row >= P.num_rows) return;\n"
            << "    const int arow = mm_actual_row(P, row);\n"
            << "    if (arow >= P.row_limit) return;\n"
-           << "    const float y = __ldg(P.ys + arow);\n"
-           << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)x; (void)y;\n"
+           << "    const float y = __ldg(P.ys + arow); (void)y;\n"
            << "    mm_tup<4> mm_ret = mm_tup<4>{};\n"
            << "    unsigned mm_rng = mm_rng_seed(col + P.region_x, arow, P.frame); (void)mm_rng;\n";
         if (have_rows) fn << rv_load.str();
+        if (e.direct_sample) fn << "    unsigned mm_word = 0; bool mm_have_word = false;\n";
         for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
         fn << body
+           << (e.direct_sample ? "    if (mm_have_word) mm_store_word(P, row + P.first_row, col, mm_word); else\n" : "")
            << "    mm_store_pixel(P, row + P.first_row, col, mm_ret);\n"
-           << "}\n";
+           << "    }\n}\n";
         if (closure_fn) {  // new_template.c.in:375-422 filter_$name, with the frame constants precomputed
             fn << "__device__ mm_tup<4> mm_closure_" << name << "(const mm_params &P, const mm_uniforms_" << name << " &U, float x, float y, float t) {\n"
                << "    const int frame = 0;\n    (void)frame; (void)x; (void)y; (void)t;\n    mm_tup<4> mm_ret = mm_tup<4>{};\n"

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -184,7 +185,10 @@ mm_image to_device_desc(const HostImage &h) {
     d.sx = h.sx; d.sy = h.sy; d.mx = h.mx; d.my = h.my;
     d.ax = h.ax; d.bx = h.bx; d.ay = h.ay; d.by = h.by;
     d.xf = h.xf; d.yf = h.yf;
-    const bool fast = d.kind == MM_IMAGE_DRAWABLE && h.w > 0 && h.h > 0 && h.w < (1 << 22) && h.h < (1 << 22);
+    // the fast paths address texel y1 * w + x1 + 0x4B000000 in 32 bits relative to fast_base
+    const bool fast = d.kind == MM_IMAGE_DRAWABLE && h.w > 0 && h.h > 0 && h.w < (1 << 22) && h.h < (1 << 22) &&
+                      (unsigned long long)h.w * (unsigned long long)h.h < 3000000000ull;
+    d.fast_base = (const unsigned *)((const char *)h.data - 4ll * 0x4B000000ll);
     d.fast_w = fast ? (float)h.w : -1.0f;
     d.fast_h = fast ? (float)h.h : -1.0f;
     d.fast_wm1 = fast ? (float)(h.w - 1) : -1.0f;
@@ -556,13 +560,15 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     P.R = (float)sqrt(2.0);
     P.bpp = inv->bpp;
     P.floatmap = floatmap;
+    P.out_mode = floatmap ? 1 : (inv->bpp == 4 ? 0 : 2);
+    P.magic23 = 0x4B000000u;
     P.edge_color_x = inv->edge_color_x;
     P.edge_color_y = inv->edge_color_y;
     for (int i = 0; i < fd.nslots; ++i) P.images[i] = fd.slots[i];
     // row pre-kernel: row-constant values are computed once per row into 4-byte arrays the pixel kernel reads
     std::vector<void *> rowvals((size_t)std::max(1, k.row_slots), nullptr);
     void *params[3] = {&P, (void *)fd.uniforms.data(), (void *)rowvals.data()};
-    unsigned gx = (unsigned)((g.region_w + 31) / 32), gy = (unsigned)((g.num_rows + 7) / 8);
+    unsigned gx = (unsigned)((g.region_w + 31) / 32), gy = (unsigned)((g.num_rows + 8 * inv->cfg.rows - 1) / (8 * inv->cfg.rows));
     if (gx == 0 || gy == 0) return;
     auto rit = lm->row_functions.find(f);
     if (rit != lm->row_functions.end()) {
@@ -833,6 +839,11 @@ mmb_invocation *mmb_invoke(mmb_module *m, int img_width, int img_height, int dev
         inv->device = device;
         inv->W = img_width;
         inv->H = img_height;
+        // tuning override for experiments (the API is mmb_set_rows_per_thread)
+        if (const char *e = getenv("MMB_ROWS_PER_THREAD")) {
+            int r = atoi(e);
+            if (r == 1 || r == 2 || r == 4 || r == 8) inv->cfg.rows = r;
+        }
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0)
@@ -898,6 +909,11 @@ int mmb_set_precise_math(mmb_invocation *inv, int enabled) { inv->cfg.precise = 
 int mmb_set_warp_shape(mmb_invocation *inv, int warp_width) {
     if (warp_width != 32 && warp_width != 16 && warp_width != 8) { set_error("warp width must be 32, 16 or 8"); return -1; }
     inv->cfg.warp_w = warp_width;
+    return 0;
+}
+int mmb_set_rows_per_thread(mmb_invocation *inv, int rows) {
+    if (rows != 1 && rows != 2 && rows != 4 && rows != 8) { set_error("rows per thread must be 1, 2, 4 or 8"); return -1; }
+    inv->cfg.rows = rows;
     return 0;
 }
 int mmb_set_edge_behaviour(mmb_invocation *inv, int mode_x, int mode_y, uint32_t color_x, uint32_t color_y) {

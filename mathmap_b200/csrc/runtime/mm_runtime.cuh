@@ -47,22 +47,28 @@
 #endif
 #define MM_BLOCK_W 32
 #define MM_BLOCK_H 8
+// MM_ROWS: a block renders MM_ROWS vertically adjacent tiles one after the other (row, row + 8, ...), so that what
+// depends on the column only (coordinate load and scaling, constant loads) is done once per thread.
+#ifndef MM_ROWS
+#define MM_ROWS 1
+#endif
 MM_DEV void mm_pixel_coords(int &col, int &row) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #if MM_WARP_W == 32
     col = blockIdx.x * MM_BLOCK_W + lane;
-    row = blockIdx.y * MM_BLOCK_H + warp;
+    row = blockIdx.y * (MM_BLOCK_H * MM_ROWS) + warp;
 #elif MM_WARP_W == 16
     col = blockIdx.x * MM_BLOCK_W + (warp & 1) * 16 + (lane & 15);
-    row = blockIdx.y * MM_BLOCK_H + (warp >> 1) * 2 + (lane >> 4);
+    row = blockIdx.y * (MM_BLOCK_H * MM_ROWS) + (warp >> 1) * 2 + (lane >> 4);
 #else
     col = blockIdx.x * MM_BLOCK_W + (warp & 3) * 8 + (lane & 7);
-    row = blockIdx.y * MM_BLOCK_H + (warp >> 2) * 4 + (lane >> 3);
+    row = blockIdx.y * (MM_BLOCK_H * MM_ROWS) + (warp >> 2) * 4 + (lane >> 3);
 #endif
 }
 #include "mm_types.h"
 #include "mm_elliptic.h"
 #include "mm_glibc_float.h"
+#include "mm_dlibm.h"
 
 template <int N> struct mm_tup { float v[N]; };
 
@@ -118,11 +124,7 @@ MM_DEV int mm_abs(int a) { return mm_d2i(fabs((double)a)); }
 #define MM_LIBM1(name, fn) MM_DEV float name(float a) { return fn##f(a); }
 #define MM_LIBM2(name, fn) MM_DEV float name(float a, float b) { return fn##f(a, b); }
 #endif
-MM_LIBM1(mm_sin, sin)
-MM_LIBM1(mm_cos, cos)
 MM_LIBM1(mm_tan, tan)
-MM_LIBM1(mm_asin, asin)
-MM_LIBM1(mm_acos, acos)
 MM_LIBM1(mm_atan, atan)
 MM_LIBM2(mm_atan2, atan2)
 MM_LIBM2(mm_pow, pow)
@@ -134,16 +136,39 @@ MM_LIBM1(mm_tanh, tanh)
 MM_LIBM1(mm_asinh, asinh)
 MM_LIBM1(mm_acosh, acosh)
 MM_LIBM1(mm_atanh, atanh)
-MM_DEV void mm_sincos(float a, float &s, float &c) {
 #if MM_PRECISE
+// sin, cos, asin, acos: mm_dlibm.h (coefficients in constant memory) for the arguments it covers, CUDA's double
+// functions for the rest (|x| >= 2^31, NaN).  Below 2^-27 the narrowed results are x and 1.
+MM_DEV void mm_sincos(float a, float &s, float &c) {
+    const float ax = fabsf(a);
+    if (ax < 7.450580596923828125e-9f) { s = a; c = 1.0f; return; }
+    if (ax < 2147483648.0f) { mm_d_sincos_core(a, s, c); return; }
     double ds, dc;
     sincos((double)a, &ds, &dc);
     s = (float)ds;
     c = (float)dc;
-#else
-    sincosf(a, &s, &c);
-#endif
 }
+MM_DEV float mm_sin(float a) {
+    const float ax = fabsf(a);
+    if (ax < 7.450580596923828125e-9f) return a;
+    if (ax < 2147483648.0f) return mm_d_sin_core(a);
+    return (float)sin((double)a);
+}
+MM_DEV float mm_cos(float a) {
+    const float ax = fabsf(a);
+    if (ax < 7.450580596923828125e-9f) return 1.0f;
+    if (ax < 2147483648.0f) return mm_d_cos_core(a);
+    return (float)cos((double)a);
+}
+MM_DEV float mm_asin(float a) { return fabsf(a) <= 1.0f ? mm_d_asin_core(a) : (float)asin((double)a); }
+MM_DEV float mm_acos(float a) { return fabsf(a) <= 1.0f ? mm_d_acos_core(a) : (float)acos((double)a); }
+#else
+MM_LIBM1(mm_sin, sin)
+MM_LIBM1(mm_cos, cos)
+MM_LIBM1(mm_asin, asin)
+MM_LIBM1(mm_acos, acos)
+MM_DEV void mm_sincos(float a, float &s, float &c) { sincosf(a, &s, &c); }
+#endif
 // GSL's gsl_sf_gamma / gsl_sf_beta are third-party and absent; tgamma/lgamma based (parity unpinned)
 MM_DEV float mm_gamma(float a) { return ((double)a > 171.0) ? 0.0f : (float)tgamma((double)a); }
 MM_DEV float mm_beta(float a, float b) { return (float)exp(lgamma((double)a) + lgamma((double)b) - lgamma((double)a + (double)b)); }
@@ -249,7 +274,7 @@ MM_DEV bool mm_c_finite(float2 z) { return isfinite(z.x) && isfinite(z.y); }
 MM_DEV float mm_cr_sinh(float x) { return mm_g_sinhf(x); }  // glibc's sinhf / coshf bit for bit (mm_glibc_float.h)
 MM_DEV float mm_cr_cosh(float x) { return mm_g_coshf(x); }
 MM_DEV void mm_cr_sincos(float x, float &s, float &c) {  // glibc: sincosf unless |x| <= FLT_MIN
-    if (fabsf(x) > MM_FLT_MIN) { double ds, dc; sincos((double)x, &ds, &dc); s = (float)ds; c = (float)dc; }
+    if (fabsf(x) > MM_FLT_MIN) mm_sincos(x, s, c);
     else { s = x; c = 1.0f; }
 }
 MM_DEV float2 mm_csqrt(float2 z) {
@@ -278,7 +303,8 @@ MM_DEV float2 mm_csqrt(float2 z) {
 }
 MM_DEV float2 mm_cexp(float2 z) {
     // glibc cexpf: expf(re) * (cosf(im), sinf(im)), each factor rounded to float first
-    float e = mm_exp(z.x), s = mm_sin(z.y), c = mm_cos(z.y);
+    float e = mm_exp(z.x), s, c;
+    mm_sincos(z.y, s, c);  // each equals the separately evaluated sinf / cosf
     return make_float2(e * c, e * s);
 }
 MM_DEV float2 mm_clog(float2 z) {
@@ -543,49 +569,56 @@ MM_DEV mm_color mm_sample_bilinear(const mm_params &P, const mm_image &img, floa
 //   * byte/255 from the rounded float directly.
 // Results are bit-identical to the generic path.
 #define MM_MAGIC_ROUND 12582912.0f  /* 1.5 * 2^23 */
-MM_DEV float mm_byte_as_float(unsigned word, unsigned sel /* 0x7650 | byte index */) {
-    return __fsub_rn(__int_as_float(__byte_perm(word, 0x4B000000u, sel)), 8388608.0f);
+// `magic` is 0x4B000000 read from mm_params: as a literal the compiler would keep it as PRMT's immediate and spend a
+// MOV per selector instead; as data it stays in one register and the selector is the immediate.
+MM_DEV float mm_byte_as_float(unsigned word, unsigned magic, unsigned sel /* 0x7650 | byte index */) {
+    return __fsub_rn(__int_as_float(__byte_perm(word, magic, sel)), 8388608.0f);
 }
 MM_DEV float mm_unit_from_rounded(float qf) {  // qf holds an integer 0..255 exactly
     return __fmaf_rn(qf, 0.003921568859368563f, __fmul_rn(qf, -2.319175823606301e-10f));
 }
-// floor of a float known to be in [0, 2^22): no conversion instructions
-MM_DEV float mm_floor_small_nonneg(float v) {
-    float r = __fsub_rn(__fadd_rn(v, 8388608.0f), 8388608.0f);  // nearest integer
-    return r > v ? __fsub_rn(r, 1.0f) : r;
-}
+// 2^23 + floor(v) for 0 <= v < 2^22, in one add rounded towards minus infinity: the low mantissa bits are floor(v) as
+// an integer, and subtracting 2^23 again (exact) gives floor(v) as a float -- no conversion instructions
+MM_DEV float mm_floor_biased(float v) { return __fadd_rd(v, 8388608.0f); }
 
-MM_DEV bool mm_bilinear_interior(const mm_params &P, const mm_image &img, float x, float y, float t, mm_tup<4> &out) {
+// WORD: instead of the four channel floats k/255, return the rounded bytes k themselves as one RGBA8 word in memory
+// order (the direct-output case, see mm_orig_val_out).
+template <bool WORD> MM_DEV bool mm_bilinear_interior(const mm_params &P, const mm_image &img, float x, float y, float t, mm_tup<4> &out, unsigned &word) {
 #if MM_EDGE_X == 0 && MM_EDGE_Y == 0
     const float px = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
     const float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
     // x1 = floor(px) in [0, w-2] and y1 in [0, h-2]  <=>  0 <= px < w-1 and 0 <= py < h-1 (w, h < 2^22: the host
     // sets the fast_* bounds to -1 otherwise).  The frame (int)t, truncated, is valid  <=>  -1 < t < num_frames.
     if (!(px >= 0.0f && px < img.fast_wm1 && py >= 0.0f && py < img.fast_hm1 && t > -1.0f && t < img.fast_nf)) return false;
-    const float fx = mm_floor_small_nonneg(px), fy = mm_floor_small_nonneg(py);
-    const unsigned x1 = (unsigned)__float_as_int(__fadd_rn(fx, 8388608.0f)) & 0x7fffffu;
-    const unsigned y1 = (unsigned)__float_as_int(__fadd_rn(fy, 8388608.0f)) & 0x7fffffu;
+    const float bx = mm_floor_biased(px), by = mm_floor_biased(py);
+    const float fx = __fsub_rn(bx, 8388608.0f), fy = __fsub_rn(by, 8388608.0f);
     const float x2f = __fsub_rn(px, fx), y2f = __fsub_rn(py, fy);
     const float x1f = __fsub_rn(1.0f, x2f), y1f = __fsub_rn(1.0f, y2f);
     const float p1 = __fmul_rn(x1f, y1f), p2 = __fmul_rn(x1f, y2f), p3 = __fmul_rn(x2f, y1f), p4 = __fmul_rn(x2f, y2f);
-    const unsigned *row0 = (const unsigned *)img.data + (y1 * (unsigned)img.w + x1);
+    // texel index y1 * w + x1, plus the 0x4B000000 of bx's exponent bits that fast_base already subtracts
+    const unsigned *row0 = img.fast_base + (((unsigned)__float_as_int(by) & 0x7fffffu) * (unsigned)img.w + (unsigned)__float_as_int(bx));
     const unsigned *row1 = row0 + img.w;
     const unsigned t1 = __ldg(row0), t3 = __ldg(row0 + 1), t2 = __ldg(row1), t4 = __ldg(row1 + 1);  // pixel1..4 of builtins.c:221-224
+    const unsigned magic = P.magic23;
+    unsigned q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {  // memory byte k is R, G, B, A
         const unsigned sel = 0x7650u | (unsigned)k;
-        const float a = mm_byte_as_float(t1, sel), b = mm_byte_as_float(t2, sel), c = mm_byte_as_float(t3, sel), d = mm_byte_as_float(t4, sel);
+        const float a = mm_byte_as_float(t1, magic, sel), b = mm_byte_as_float(t2, magic, sel), c = mm_byte_as_float(t3, magic, sel),
+                    d = mm_byte_as_float(t4, magic, sel);
         const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, p1), __fmul_rn(b, p2)), __fmul_rn(c, p3)), __fmul_rn(d, p4));
-        const float qf = __fsub_rn(__fadd_rn(s, MM_MAGIC_ROUND), MM_MAGIC_ROUND);  // rintf(s), 0 <= s < 256
-        out.v[k] = mm_unit_from_rounded(qf);
+        const float biased = __fadd_rn(s, MM_MAGIC_ROUND);  // 1.5 * 2^23 + rintf(s), 0 <= s < 256: the low mantissa byte is (int)rintf(s) & 0xff
+        if (WORD) q[k] = (unsigned)__float_as_int(biased);
+        else out.v[k] = mm_unit_from_rounded(__fsub_rn(biased, MM_MAGIC_ROUND));
     }
+    if (WORD) word = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
     return true;
 #else
     return false;
 #endif
 }
 
-MM_DEV bool mm_nearest_interior(const mm_params &P, const mm_image &img, float x, float y, float t, mm_tup<4> &out) {
+template <bool WORD> MM_DEV bool mm_nearest_interior(const mm_params &P, const mm_image &img, float x, float y, float t, mm_tup<4> &out, unsigned &word) {
 #if MM_EDGE_X == 0 && MM_EDGE_Y == 0
     float px = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
     float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
@@ -594,11 +627,12 @@ MM_DEV bool mm_nearest_interior(const mm_params &P, const mm_image &img, float x
     py = __fadd_rn(py, 0.5f);
 #endif
     if (!(px >= 0.0f && px < img.fast_w && py >= 0.0f && py < img.fast_h && t > -1.0f && t < img.fast_nf)) return false;
-    const unsigned x1 = (unsigned)__float_as_int(__fadd_rn(mm_floor_small_nonneg(px), 8388608.0f)) & 0x7fffffu;
-    const unsigned y1 = (unsigned)__float_as_int(__fadd_rn(mm_floor_small_nonneg(py), 8388608.0f)) & 0x7fffffu;
-    const unsigned texel = __ldg((const unsigned *)img.data + (y1 * (unsigned)img.w + x1));
+    const unsigned xb = (unsigned)__float_as_int(mm_floor_biased(px)), yb = (unsigned)__float_as_int(mm_floor_biased(py));
+    const unsigned texel = __ldg(img.fast_base + ((yb & 0x7fffffu) * (unsigned)img.w + xb));
+    if (WORD) { word = texel; return true; }
+    const unsigned magic = P.magic23;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out.v[k] = mm_unit_from_rounded(mm_byte_as_float(texel, 0x7650u | (unsigned)k));
+    for (int k = 0; k < 4; ++k) out.v[k] = mm_unit_from_rounded(mm_byte_as_float(texel, magic, 0x7650u | (unsigned)k));
     return true;
 #else
     return false;
@@ -628,16 +662,37 @@ MM_DEV mm_tup<4> mm_orig_val(const mm_params &P, int image, float x, float y, fl
     if (img.kind == MM_IMAGE_CLOSURE) return mm_closure_dispatch(P, img, x, y, t);  // img->v.closure.func, opmacros.h:208
     mm_tup<4> r;
 #if MM_AA
-    if (mm_bilinear_interior(P, img, x, y, t, r)) return r;
+    unsigned unused;
+    if (mm_bilinear_interior<false>(P, img, x, y, t, r, unused)) return r;
     return mm_tuple_from_color(mm_sample_bilinear(P, img, x, y, mm_f2i(t)));
 #else
-    if (mm_nearest_interior(P, img, x, y, t, r)) return r;
+    unsigned unused;
+    if (mm_nearest_interior<false>(P, img, x, y, t, r, unused)) return r;
     return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, mm_f2i(t)));
 #endif
 }
 // the nearest sampler regardless of MM_AA: render_image of a drawable (builtins.c:306)
 MM_DEV mm_tup<4> mm_orig_val_nearest(const mm_params &P, const mm_image &img, float x, float y) {
     return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, 0));
+}
+
+// ORIG_VAL whose result is the pixel itself (cuda_emit.cpp: find_direct_output).  For RGBA8 output of a drawable's
+// interior the sample's rounded bytes ARE the output bytes: the reference turns byte k into (float)(k / 255.0), clamps,
+// multiplies by 255.0 in double and truncates, which gives k back for every k in 0..255 (tests/test_cabi.py checks the
+// 256 cases), so the conversion to floats and back is skipped.  Everything else takes the general path.
+MM_DEV mm_tup<4> mm_orig_val_out(const mm_params &P, int image, float x, float y, float t, unsigned &word, bool &have_word) {
+    const mm_image &img = P.images[image];
+    if (P.out_mode == 0 && img.kind == MM_IMAGE_DRAWABLE) {
+        mm_tup<4> r = mm_tup<4>{};
+#if MM_AA
+        have_word = mm_bilinear_interior<true>(P, img, __fmul_rn(x, img.xf), __fmul_rn(y, img.yf), t, r, word);
+#else
+        have_word = mm_nearest_interior<true>(P, img, __fmul_rn(x, img.xf), __fmul_rn(y, img.yf), t, r, word);
+#endif
+        if (have_word) return r;
+    }
+    have_word = false;
+    return mm_orig_val(P, image, x, y, t);
 }
 
 // local (compact) row of this launch -> absolute image row
@@ -649,16 +704,23 @@ MM_DEV int mm_actual_row(const mm_params &P, int row) {
 // ----------------------------------------------------------------------- output
 // new_template.c.in:272-293: clamp, times 255.0 in double, truncate
 MM_DEV unsigned mm_quant(float v) { return __float2uint_rz(__fmul_rz(mm_clamp01(v), 255.0f)); }
+// The same byte in the low mantissa bits of a float: fma(v, 255, 2^23) rounded towards zero is 2^23 + floor(v * 255) with the
+// product exact inside the fma, i.e. the truncated double product of the reference -- one FP32 instruction, no conversion
+MM_DEV unsigned mm_quant_bits(float v) { return (unsigned)__float_as_int(__fmaf_rz(mm_clamp01(v), 255.0f, 8388608.0f)); }
 
+MM_DEV void mm_store_word(const mm_params &P, int row, int col, unsigned word) {  // out_mode 0 only
+    ((unsigned *)((char *)P.out + (size_t)(row - P.first_row) * (size_t)P.out_stride))[col] = word;
+}
 MM_DEV void mm_store_pixel(const mm_params &P, int row, int col, const mm_tup<4> &t) {
     char *rowp = (char *)P.out + (size_t)(row - P.first_row) * (size_t)P.out_stride;
-    if (P.floatmap) {
-        ((float4 *)rowp)[col] = make_float4(t.v[0], t.v[1], t.v[2], t.v[3]);
+    if (P.out_mode == 0) {  // RGBA8
+        const unsigned rg = __byte_perm(mm_quant_bits(t.v[0]), mm_quant_bits(t.v[1]), 0x0040);
+        const unsigned ba = __byte_perm(mm_quant_bits(t.v[2]), mm_quant_bits(t.v[3]), 0x0040);
+        ((unsigned *)rowp)[col] = __byte_perm(rg, ba, 0x5410);
         return;
     }
-    if (P.bpp == 4) {
-        unsigned w = mm_quant(t.v[0]) | (mm_quant(t.v[1]) << 8) | (mm_quant(t.v[2]) << 16) | (mm_quant(t.v[3]) << 24);
-        ((unsigned *)rowp)[col] = w;
+    if (P.out_mode == 1) {
+        ((float4 *)rowp)[col] = make_float4(t.v[0], t.v[1], t.v[2], t.v[3]);
         return;
     }
     unsigned char *p = (unsigned char *)rowp + (size_t)col * P.bpp;

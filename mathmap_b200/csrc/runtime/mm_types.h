@@ -21,6 +21,9 @@ struct mm_image {
     // Bounds of the samplers' interior fast paths as floats, filled by the host: w, h, w-1, h-1 and num_frames
     // when w, h < 2^22 and the image is a drawable, else all -1 (the fast-path tests then never hold).
     float fast_w, fast_h, fast_wm1, fast_hm1, fast_nf;
+    // data - 0x4B000000 texels: the fast paths index texels with the raw bits of 2^23 + x1 (a float whose mantissa holds
+    // the column), so the offset of the exponent bits is taken out of the base once, by the host
+    const unsigned *fast_base;
     int closure_filter;    // MM_IMAGE_CLOSURE: which filter; `data` then points at that filter's packed uniforms (device memory)
 };
 
@@ -41,6 +44,8 @@ struct mm_params {
     float R;
     int bpp;
     int floatmap;
+    int out_mode;             // 0: RGBA8 (bpp 4), 1: floatmap, 2: bpp 1..3 -- one test in the store instead of two
+    unsigned magic23;         // 0x4B000000 (2^23 as float bits); passed as data so that byte -> float PRMTs keep it in a register
     mm_color edge_color_x, edge_color_y;
     mm_image images[MM_MAX_IMAGES];
 };

@@ -66,3 +66,15 @@ def test_nvrtc_compiles_for_sm100a_without_gpu():
             assert m.compile_check(antialiasing=True, precise=precise) > 10000
     src = mb.Module(source=filter_source("examples/Distorts/Twirl.mm")).cuda_source
     assert "mm_kernel_twirl" in src and "mm_orig_val" in src and "__grid_constant__" in src
+
+
+def test_byte_unit_byte_round_trip_is_identity():
+    """The direct-output fast path (mm_orig_val_out) stores a sample's rounded bytes without converting them to floats
+    and back.  That is exact because the reference's own chain -- (float)(k / 255.0) (opmacros.h:147-150), clamp,
+    times 255.0 in double, truncate (new_template.c.in:281-292) -- returns k for every byte k."""
+    import numpy as np
+    k = np.arange(256)
+    unit = (k / 255.0).astype(np.float32)
+    clamped = np.maximum(np.float32(0), np.minimum(np.float32(1), unit))
+    back = (clamped.astype(np.float64) * 255.0).astype(np.uint8)
+    assert (back == k).all()
