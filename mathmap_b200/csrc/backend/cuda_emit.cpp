@@ -636,6 +636,18 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         rv << "};\n";
         const bool have_rows = use_rows && k.row_slots > 0;
         if (have_rows) k.row_kernel_name = "mm_rows_" + name;
+        // Straight-line pixel code gains from rendering several tiles per block (the per-column work and the constant
+        // loads are shared); loops (escape-time iteration, Droste levels) make tiles uneven and measured slower that way.
+        {
+            std::function<bool(const Stmt *)> has_loop = [&](const Stmt *st) {
+                for (; st; st = st->next) {
+                    if (st->kind == ST_WHILE && st->level >= 1) return true;
+                    if (st->kind == ST_IF && (has_loop(st->cons) || has_loop(st->alt))) return true;
+                }
+                return false;
+            };
+            k.auto_rows = has_loop(code->first) ? 1 : 4;
+        }
 
         std::ostringstream fn;
         fn << st.str() << rv.str();
@@ -654,12 +666,13 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H) " << k.kernel_name << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
            << name << " U, const __grid_constant__ mm_rowvals_" << name << " RV) {\n"
            << "    int col, mm_row0;\n"
-           << "    mm_pixel_coords(col, mm_row0);\n"
+           << "    constexpr int mm_rows = MM_ROWS ? MM_ROWS : " << k.auto_rows << ";\n"
+           << "    mm_pixel_coords(col, mm_row0, mm_rows);\n"
            << "    if (col >= P.region_w) return;\n"
            << "    const float x = __ldg(P.xs + (col + P.region_x));\n"
            << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)x;\n"
            << "#pragma unroll 1\n"
-           << "    for (int mm_rep = 0; mm_rep < MM_ROWS; ++mm_rep) {\n"
+           << "    for (int mm_rep = 0; mm_rep < mm_rows; ++mm_rep) {\n"
            << "    const int row = mm_row0 + mm_rep * MM_BLOCK_H;\n"
            << "    if (row >= P.num_rows) return;\n"
            << "    const int arow = mm_actual_row(P, row);\n"

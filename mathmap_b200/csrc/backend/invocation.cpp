@@ -568,7 +568,11 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     // row pre-kernel: row-constant values are computed once per row into 4-byte arrays the pixel kernel reads
     std::vector<void *> rowvals((size_t)std::max(1, k.row_slots), nullptr);
     void *params[3] = {&P, (void *)fd.uniforms.data(), (void *)rowvals.data()};
-    unsigned gx = (unsigned)((g.region_w + 31) / 32), gy = (unsigned)((g.num_rows + 8 * inv->cfg.rows - 1) / (8 * inv->cfg.rows));
+    unsigned gx = (unsigned)((g.region_w + 31) / 32), gy;
+    {
+        const int rows = inv->cfg.rows ? inv->cfg.rows : k.auto_rows;
+        gy = (unsigned)((g.num_rows + 8 * rows - 1) / (8 * rows));
+    }
     if (gx == 0 || gy == 0) return;
     auto rit = lm->row_functions.find(f);
     if (rit != lm->row_functions.end()) {
@@ -912,7 +916,7 @@ int mmb_set_warp_shape(mmb_invocation *inv, int warp_width) {
     return 0;
 }
 int mmb_set_rows_per_thread(mmb_invocation *inv, int rows) {
-    if (rows != 1 && rows != 2 && rows != 4 && rows != 8) { set_error("rows per thread must be 1, 2, 4 or 8"); return -1; }
+    if (rows != 0 && rows != 1 && rows != 2 && rows != 4 && rows != 8) { set_error("rows per thread must be 0 (automatic), 1, 2, 4 or 8"); return -1; }
     inv->cfg.rows = rows;
     return 0;
 }

@@ -16,7 +16,7 @@ namespace mmbackend {
 void set_error(const std::string &msg);
 
 struct KernelConfig {
-    int aa = 0, supersampling = 0, edge_x = 0, edge_y = 0, precise = 1, warp_w = 32, rows = 1;  // rows: tile rows one thread renders in sequence
+    int aa = 0, supersampling = 0, edge_x = 0, edge_y = 0, precise = 1, warp_w = 32, rows = 0;  // rows: 32x8 tiles a block renders in sequence, 0 = the emitter's choice per kernel
     std::string key() const;
 };
 

@@ -49,20 +49,21 @@
 #define MM_BLOCK_H 8
 // MM_ROWS: a block renders MM_ROWS vertically adjacent tiles one after the other (row, row + 8, ...), so that what
 // depends on the column only (coordinate load and scaling, constant loads) is done once per thread.
+// MM_ROWS 0: each kernel uses the count the emitter chose for it.
 #ifndef MM_ROWS
-#define MM_ROWS 1
+#define MM_ROWS 0
 #endif
-MM_DEV void mm_pixel_coords(int &col, int &row) {
+MM_DEV void mm_pixel_coords(int &col, int &row, int rows) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #if MM_WARP_W == 32
     col = blockIdx.x * MM_BLOCK_W + lane;
-    row = blockIdx.y * (MM_BLOCK_H * MM_ROWS) + warp;
+    row = blockIdx.y * (MM_BLOCK_H * rows) + warp;
 #elif MM_WARP_W == 16
     col = blockIdx.x * MM_BLOCK_W + (warp & 1) * 16 + (lane & 15);
-    row = blockIdx.y * (MM_BLOCK_H * MM_ROWS) + (warp >> 1) * 2 + (lane >> 4);
+    row = blockIdx.y * (MM_BLOCK_H * rows) + (warp >> 1) * 2 + (lane >> 4);
 #else
     col = blockIdx.x * MM_BLOCK_W + (warp & 3) * 8 + (lane & 7);
-    row = blockIdx.y * (MM_BLOCK_H * MM_ROWS) + (warp >> 2) * 4 + (lane >> 3);
+    row = blockIdx.y * (MM_BLOCK_H * rows) + (warp >> 2) * 4 + (lane >> 3);
 #endif
 }
 #include "mm_types.h"

@@ -7,8 +7,8 @@ import mathmap_b200 as mb
 m = mb.Module.from_file(sys.argv[1])
 aa = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 precise = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-rows = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-src = m.cuda_source.replace("#define MM_AA 0", "#define MM_AA %d" % aa).replace("#define MM_PRECISE 1", "#define MM_PRECISE %d" % precise).replace("#define MM_ROWS 1", "#define MM_ROWS %d" % rows)
+rows = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+src = m.cuda_source.replace("#define MM_AA 0", "#define MM_AA %d" % aa).replace("#define MM_PRECISE 1", "#define MM_PRECISE %d" % precise).replace("#define MM_ROWS 0", "#define MM_ROWS %d" % rows)
 d = tempfile.mkdtemp()
 open(os.path.join(d, "k.cu"), "w").write(src)
 rt = os.path.join(ROOT, "mathmap_b200", "csrc", "runtime")
