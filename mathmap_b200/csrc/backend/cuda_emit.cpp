@@ -216,7 +216,13 @@ struct Emitter {
         case OP_ACOS: return fn1("mm_acos");
         case OP_ATAN: return fn1("mm_atan");
         case OP_ATAN2: return fn2("mm_atan2");
-        case OP_POW: return fn2("mm_pow");
+        case OP_POW: {
+            // pow(x, 2): x * x is exact in double for a float x and the host's pow returns exactly representable results
+            // exactly (its error bound is below one ulp), so the narrowed value is the correctly rounded float product
+            const Primary &ex = r->args[1];
+            if (ex.is_const && ((ex.c.type == T_INT && ex.c.i == 2) || (ex.c.type == T_FLOAT && ex.c.f == 2.0f))) return "mm_sqr(" + F(0) + ")";
+            return fn2("mm_pow");
+        }
         case OP_EXP: return fn1("mm_exp");
         case OP_LOG: return fn1("mm_log");
         case OP_SINH: return fn1("mm_sinh");

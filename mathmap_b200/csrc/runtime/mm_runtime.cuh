@@ -113,6 +113,7 @@ MM_DEV float mm_hypot(float a, float b) {
     double s = __dadd_rn(__dmul_rn((double)a, (double)a), __dmul_rn((double)b, (double)b));
     return (float)__dsqrt_rn(s);
 }
+MM_DEV float mm_sqr(float a) { return __fmul_rn(a, a); }  // == (float)pow((double)a, 2.0), see cuda_emit.cpp OP_POW
 MM_DEV int mm_floor(float a) { return mm_f2i(floorf(a)); }
 MM_DEV int mm_ceil(float a) { return mm_f2i(ceilf(a)); }
 MM_DEV float mm_abs(float a) { return fabsf(a); }
@@ -126,11 +127,7 @@ MM_DEV int mm_abs(int a) { return mm_d2i(fabs((double)a)); }
 #define MM_LIBM2(name, fn) MM_DEV float name(float a, float b) { return fn##f(a, b); }
 #endif
 MM_LIBM1(mm_tan, tan)
-MM_LIBM1(mm_atan, atan)
-MM_LIBM2(mm_atan2, atan2)
 MM_LIBM2(mm_pow, pow)
-MM_LIBM1(mm_exp, exp)
-MM_LIBM1(mm_log, log)
 MM_LIBM1(mm_sinh, sinh)
 MM_LIBM1(mm_cosh, cosh)
 MM_LIBM1(mm_tanh, tanh)
@@ -161,11 +158,24 @@ MM_DEV float mm_cos(float a) {
     if (ax < 2147483648.0f) return mm_d_cos_core(a);
     return (float)cos((double)a);
 }
+// RN_float(exp(x)) is +inf above 88.73 and 0 below -103.98
+MM_DEV float mm_exp(float a) { return a > 89.0f ? __int_as_float(0x7f800000) : (a < -104.0f ? 0.0f : mm_d_exp_core(a)); }
+MM_DEV float mm_log(float a) { return (a > 0.0f && a < __int_as_float(0x7f800000)) ? mm_d_log_core(a) : (float)log((double)a); }
+MM_DEV float mm_atan(float a) { return a == a ? mm_d_atan_core(a) : (float)atan((double)a); }
+MM_DEV float mm_atan2(float y, float x) {
+    const float ay = fabsf(y), ax = fabsf(x), inf = __int_as_float(0x7f800000);
+    if (ay > 0.0f && ay < inf && ax > 0.0f && ax < inf) return mm_d_atan2_core(y, x);
+    return (float)atan2((double)y, (double)x);  // zeros, infinities, NaN: the special cases of the standard
+}
 MM_DEV float mm_asin(float a) { return fabsf(a) <= 1.0f ? mm_d_asin_core(a) : (float)asin((double)a); }
 MM_DEV float mm_acos(float a) { return fabsf(a) <= 1.0f ? mm_d_acos_core(a) : (float)acos((double)a); }
 #else
 MM_LIBM1(mm_sin, sin)
 MM_LIBM1(mm_cos, cos)
+MM_LIBM1(mm_exp, exp)
+MM_LIBM1(mm_log, log)
+MM_LIBM1(mm_atan, atan)
+MM_LIBM2(mm_atan2, atan2)
 MM_LIBM1(mm_asin, asin)
 MM_LIBM1(mm_acos, acos)
 MM_DEV void mm_sincos(float a, float &s, float &c) { sincosf(a, &s, &c); }
@@ -308,6 +318,8 @@ MM_DEV float2 mm_cexp(float2 z) {
     mm_sincos(z.y, s, c);  // each equals the separately evaluated sinf / cosf
     return make_float2(e * c, e * s);
 }
+// logf, correctly rounded, in both math modes (the argument is positive and finite here)
+MM_DEV float mm_log_cr(float a) { return (a > 0.0f && a < __int_as_float(0x7f800000)) ? mm_d_log_core(a) : (float)log((double)a); }
 MM_DEV float2 mm_clog(float2 z) {
     // s_clog_template.c without its scaling of huge / subnormal arguments
     float ax = fabsf(z.x), ay = fabsf(z.y);
@@ -328,7 +340,7 @@ MM_DEV float2 mm_clog(float2 z) {
         const double d = __dsub_rn(__dadd_rn(__dmul_rn((double)ax, (double)ax), __dmul_rn((double)ay, (double)ay)), 1.0);
         re = __fmul_rn(mm_g_log1pf((float)d), 0.5f);
     } else
-        re = (float)log((double)mm_hypot(ax, ay));
+        re = mm_log_cr(mm_hypot(ax, ay));
     return make_float2(re, mm_g_atan2f(z.y, z.x));
 }
 MM_DEV float mm_carg(float2 z) { return mm_g_atan2f(z.y, z.x); }  // cargf = atan2f, ops.lisp:205
