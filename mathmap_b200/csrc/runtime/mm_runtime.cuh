@@ -652,6 +652,41 @@ template <bool WORD> MM_DEV bool mm_nearest_interior(const mm_params &P, const m
 #endif
 }
 
+// ---- exterior fast paths ---------------------------------------------------------
+// A sample whose texels ALL lie outside the image in x gets the x edge colour from every texel (x is tested first,
+// builtins.c:121-130), one whose columns are all inside but whose rows are all outside the y edge colour.  For the
+// bilinear sampler the blend of four equal bytes c is c again: the float weights sum to 1 within 4 * 2^-24 and the
+// seven roundings add less than 2^-21 relative, so |s - c| < 3e-4 and rintf(s) = c (tests/test_cabi.py checks the bound).  Filters that recurse until a
+// tap lands inside the picture (Droste) take this path for most of their taps.  NaN coordinates fail every test.
+MM_DEV mm_tup<4> mm_tuple_from_edge(mm_color c) { return mm_tuple_from_color(c); }
+MM_DEV bool mm_bilinear_exterior(const mm_params &P, const mm_image &img, float x, float y, mm_color &edge) {
+#if MM_EDGE_X == 0 && MM_EDGE_Y == 0
+    if (!(img.fast_w > 0.0f)) return false;
+    const float px = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
+    const float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
+    // beyond +-2^31 the reference's (int) casts saturate and its weights px - (float)x1 are no longer in [0, 1]: general path
+    if (!(fabsf(px) < 2147483648.0f && fabsf(py) < 2147483648.0f)) return false;
+    // x1 = floor(px) and x1 + 1 both outside [0, w)  <=>  px < -1 or px >= w
+    if (px < -1.0f || px >= img.fast_w) { edge = P.edge_color_x; return true; }
+    if (px >= 0.0f && px < img.fast_wm1 && (py < -1.0f || py >= img.fast_h)) { edge = P.edge_color_y; return true; }
+#endif
+    return false;
+}
+MM_DEV bool mm_nearest_exterior(const mm_params &P, const mm_image &img, float x, float y, mm_color &edge) {
+#if MM_EDGE_X == 0 && MM_EDGE_Y == 0
+    if (!(img.fast_w > 0.0f)) return false;
+    float px = __fmul_rn(__fadd_rn(x, img.mx), img.sx);
+    float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
+#if !MM_SUPERSAMPLING
+    px = __fadd_rn(px, 0.5f);
+    py = __fadd_rn(py, 0.5f);
+#endif
+    if (px < 0.0f || px >= img.fast_w) { edge = P.edge_color_x; return true; }
+    if (py < 0.0f || py >= img.fast_h) { edge = P.edge_color_y; return true; }
+#endif
+    return false;
+}
+
 // get_floatmap_pixel, builtins.c:249-265: nearest via lrintf (round half even)
 MM_DEV mm_tup<4> mm_floatmap_pixel(const mm_image &img, float x, float y) {
     mm_tup<4> t;
@@ -677,10 +712,14 @@ MM_DEV mm_tup<4> mm_orig_val(const mm_params &P, int image, float x, float y, fl
 #if MM_AA
     unsigned unused;
     if (mm_bilinear_interior<false>(P, img, x, y, t, r, unused)) return r;
+    mm_color edge;
+    if (mm_bilinear_exterior(P, img, x, y, edge)) return mm_tuple_from_edge(edge);
     return mm_tuple_from_color(mm_sample_bilinear(P, img, x, y, mm_f2i(t)));
 #else
     unsigned unused;
     if (mm_nearest_interior<false>(P, img, x, y, t, r, unused)) return r;
+    mm_color edge;
+    if (mm_nearest_exterior(P, img, x, y, edge)) return mm_tuple_from_edge(edge);
     return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, mm_f2i(t)));
 #endif
 }
@@ -698,9 +737,14 @@ MM_DEV mm_tup<4> mm_orig_val_out(const mm_params &P, int image, float x, float y
     if (P.out_mode == 0 && img.kind == MM_IMAGE_DRAWABLE) {
         mm_tup<4> r = mm_tup<4>{};
 #if MM_AA
-        have_word = mm_bilinear_interior<true>(P, img, __fmul_rn(x, img.xf), __fmul_rn(y, img.yf), t, r, word);
+        const float xs = __fmul_rn(x, img.xf), ys = __fmul_rn(y, img.yf);
+        mm_color edge;
+#if MM_AA
+        have_word = mm_bilinear_interior<true>(P, img, xs, ys, t, r, word);
+        if (!have_word && mm_bilinear_exterior(P, img, xs, ys, edge)) { word = __byte_perm(edge, 0, 0x0123); have_word = true; }
 #else
-        have_word = mm_nearest_interior<true>(P, img, __fmul_rn(x, img.xf), __fmul_rn(y, img.yf), t, r, word);
+        have_word = mm_nearest_interior<true>(P, img, xs, ys, t, r, word);
+        if (!have_word && mm_nearest_exterior(P, img, xs, ys, edge)) { word = __byte_perm(edge, 0, 0x0123); have_word = true; }
 #endif
         if (have_word) return r;
     }

@@ -78,3 +78,23 @@ def test_byte_unit_byte_round_trip_is_identity():
     clamped = np.maximum(np.float32(0), np.minimum(np.float32(1), unit))
     back = (clamped.astype(np.float64) * 255.0).astype(np.uint8)
     assert (back == k).all()
+
+
+def test_bilinear_blend_of_equal_bytes_returns_the_byte():
+    """The exterior fast path of the bilinear sampler (mm_bilinear_exterior) returns the edge colour without blending.
+    In the reference the four texels are then the same byte c and the blend ((c*p1 + c*p2) + c*p3) + c*p4 in float
+    arithmetic (builtins.c:226-240), rounded with rintf, must give c: checked over random sub-pixel positions."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    f32 = np.float32
+    px = (rng.random(200000) * 4096).astype(f32)
+    py = (rng.random(200000) * 4096).astype(f32)
+    x2f = px - np.floor(px).astype(f32)
+    y2f = py - np.floor(py).astype(f32)
+    x1f = (f32(1.0) - x2f).astype(f32)
+    y1f = (f32(1.0) - y2f).astype(f32)
+    p1, p2, p3, p4 = x1f * y1f, x1f * y2f, x2f * y1f, x2f * y2f
+    for c in (0, 1, 127, 128, 254, 255):
+        cf = f32(c)
+        s = ((cf * p1 + cf * p2).astype(f32) + cf * p3).astype(f32) + cf * p4
+        assert (np.rint(s.astype(f32)) == c).all()

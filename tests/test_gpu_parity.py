@@ -107,7 +107,7 @@ def test_bands_equal_whole():
     assert inv.calc_lines(10, 10).shape[0] == 0
 
 
-@pytest.mark.parametrize("mode_x,mode_y", [(1, 1), (2, 2), (3, 3), (1, 2), (0, 3)])
+@pytest.mark.parametrize("mode_x,mode_y", [(0, 0), (1, 1), (2, 2), (3, 3), (1, 2), (0, 3)])
 def test_edge_behaviours(mode_x, mode_y):
     img = synthetic_rgba(97, 61)
     m = mb.Module(source=filter_source("examples/Geometry/Zoom.mm"))
@@ -120,6 +120,25 @@ def test_edge_behaviours(mode_x, mode_y):
         want = OracleFilter(m.ir).render(97, 61, {"in": img, "factor": 0.37}, antialiasing=aa, edge_behaviour=(mode_x, mode_y),
                                          edge_colors=(0x11223344, 0x55667788))
         assert np.array_equal(got, want), "edge modes %d/%d aa=%d" % (mode_x, mode_y, aa)
+
+
+@pytest.mark.parametrize("aa", [False, True])
+def test_samples_outside_the_image_take_the_edge_colours(aa):
+    """Taps with every texel outside the picture (the samplers' exterior fast paths) and taps straddling the border (general
+    path), with distinct non-zero edge colours, through a filter that post-processes the sample (tuple path) and one
+    whose pixel is the sample itself (direct RGBA8 output), and into a floatmap."""
+    img = synthetic_rgba(83, 59)
+    post = "filter outside (image in)\n  c = in(xy*3.1+xy:[0.3,0.2]);\n  rgba:[1-c[0], c[1]*0.5, c[2], c[3]]\nend\n"
+    direct = "filter outside2 (image in)\n  in(xy*2.3+xy:[-0.4,0.1])\nend\n"
+    for src in (post, direct):
+        m = mb.Module(source=src)
+        for floatmap in (False, True):
+            inv = mb.Invocation(m, 83, 59, antialiasing=aa, precise=True)
+            inv.set("in", img)
+            inv.set_edge_behaviour(0, 0, 0x11223344, 0xa5667788)
+            got = inv.render(0, 0.0, floatmap=floatmap)
+            want = OracleFilter(m.ir).render(83, 59, {"in": img}, antialiasing=aa, edge_colors=(0x11223344, 0xa5667788), floatmap=floatmap)
+            assert np.array_equal(got, want), "aa=%d floatmap=%d %s" % (aa, floatmap, src.split()[1])
 
 
 def test_supersampling():
