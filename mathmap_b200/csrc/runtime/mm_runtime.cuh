@@ -736,7 +736,6 @@ MM_DEV mm_tup<4> mm_orig_val_out(const mm_params &P, int image, float x, float y
     const mm_image &img = P.images[image];
     if (P.out_mode == 0 && img.kind == MM_IMAGE_DRAWABLE) {
         mm_tup<4> r = mm_tup<4>{};
-#if MM_AA
         const float xs = __fmul_rn(x, img.xf), ys = __fmul_rn(y, img.yf);
         mm_color edge;
 #if MM_AA
