@@ -47,7 +47,8 @@ WORKLOADS = {
 MANDELBROT_FLOPS_PER_ITERATION = 39
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full captures, profiles/r01_*_ncu_full.txt
 # (gauss: the dominant kernel of its four launches, the row pass of the IIR)
-NCU_TRAFFIC_BYTES = {"mandelbrot": 6.96e6 + 1.0171e9, "twirl": 241.8e6 + 229.4e6, "droste": 212.1e6 + 224.0e6, "gauss": 4.238e9 + 3.194e9}
+NCU_TRAFFIC_BYTES = {"mandelbrot": 2.70e6 + 1.0156e9, "twirl": 241.8e6 + 227.8e6, "droste": 210.8e6 + 227.1e6, "gauss": 4.257e9 + 3.195e9,
+                     "sea": 32.6e6 + 1.1e6, "ident": 268.5e6 + 230.9e6}
 B200_SMS, FP32_LANES_PER_SM = 148, 128
 
 

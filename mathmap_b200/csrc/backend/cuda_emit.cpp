@@ -677,11 +677,16 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
            << "    if (col >= P.region_w) return;\n"
            << "    const float x = __ldg(P.xs + (col + P.region_x));\n"
            << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)x;\n"
+           << "    // tile k of this block: compact row mm_row0 + 8 k, absolute row mm_arow0 + k * mm_astep (8-row blocks may be interleaved over\n"
+           << "    // ranks), output row pointer advancing by 8 rows -- all loop-invariant work is done here, once\n"
+           << "    const int mm_arow0 = mm_actual_row(P, mm_row0), mm_astep = MM_BLOCK_H * (P.row_interleave > 1 ? P.row_interleave : 1);\n"
+           << "    char *mm_outp = (char *)P.out + (size_t)mm_row0 * (size_t)P.out_stride;\n"
+           << "    const size_t mm_ostep = (size_t)MM_BLOCK_H * (size_t)P.out_stride;\n"
            << "#pragma unroll 1\n"
-           << "    for (int mm_rep = 0; mm_rep < mm_rows; ++mm_rep) {\n"
+           << "    for (int mm_rep = 0; mm_rep < mm_rows; ++mm_rep, mm_outp += mm_ostep) {\n"
            << "    const int row = mm_row0 + mm_rep * MM_BLOCK_H;\n"
            << "    if (row >= P.num_rows) return;\n"
-           << "    const int arow = mm_actual_row(P, row);\n"
+           << "    const int arow = mm_arow0 + mm_rep * mm_astep;\n"
            << "    if (arow >= P.row_limit) return;\n"
            << "    const float y = __ldg(P.ys + arow); (void)y;\n"
            << "    mm_tup<4> mm_ret = mm_tup<4>{};\n"
@@ -690,8 +695,8 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         if (e.direct_sample) fn << "    unsigned mm_word = 0; bool mm_have_word = false;\n";
         for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
         fn << body
-           << (e.direct_sample ? "    if (mm_have_word) mm_store_word(P, row + P.first_row, col, mm_word); else\n" : "")
-           << "    mm_store_pixel(P, row + P.first_row, col, mm_ret);\n"
+           << (e.direct_sample ? "    if (mm_have_word) mm_store_word(mm_outp, col, mm_word); else\n" : "")
+           << "    mm_store_pixel(P, mm_outp, col, mm_ret);\n"
            << "    }\n}\n";
         if (closure_fn) {  // new_template.c.in:375-422 filter_$name, with the frame constants precomputed
             fn << "__device__ mm_tup<4> mm_closure_" << name << "(const mm_params &P, const mm_uniforms_" << name << " &U, float x, float y, float t) {\n"

@@ -728,6 +728,10 @@ MM_DEV mm_tup<4> mm_orig_val_nearest(const mm_params &P, const mm_image &img, fl
     return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, 0));
 }
 
+// The general ORIG_VAL as a real call: keeps everything but the interior fast path out of the pixel loop of a
+// direct-output kernel (inlined, its branches cost the hot path about ten instructions of convergence bookkeeping).
+__device__ __noinline__ mm_tup<4> mm_orig_val_call(const mm_params &P, int image, float x, float y, float t) { return mm_orig_val(P, image, x, y, t); }
+
 // ORIG_VAL whose result is the pixel itself (cuda_emit.cpp: find_direct_output).  For RGBA8 output of a drawable's
 // interior the sample's rounded bytes ARE the output bytes: the reference turns byte k into (float)(k / 255.0), clamps,
 // multiplies by 255.0 in double and truncates, which gives k back for every k in 0..255 (tests/test_cabi.py checks the
@@ -737,18 +741,15 @@ MM_DEV mm_tup<4> mm_orig_val_out(const mm_params &P, int image, float x, float y
     if (P.out_mode == 0 && img.kind == MM_IMAGE_DRAWABLE) {
         mm_tup<4> r = mm_tup<4>{};
         const float xs = __fmul_rn(x, img.xf), ys = __fmul_rn(y, img.yf);
-        mm_color edge;
 #if MM_AA
         have_word = mm_bilinear_interior<true>(P, img, xs, ys, t, r, word);
-        if (!have_word && mm_bilinear_exterior(P, img, xs, ys, edge)) { word = __byte_perm(edge, 0, 0x0123); have_word = true; }
 #else
         have_word = mm_nearest_interior<true>(P, img, xs, ys, t, r, word);
-        if (!have_word && mm_nearest_exterior(P, img, xs, ys, edge)) { word = __byte_perm(edge, 0, 0x0123); have_word = true; }
 #endif
         if (have_word) return r;
     }
     have_word = false;
-    return mm_orig_val(P, image, x, y, t);
+    return mm_orig_val_call(P, image, x, y, t);
 }
 
 // local (compact) row of this launch -> absolute image row
@@ -764,11 +765,9 @@ MM_DEV unsigned mm_quant(float v) { return __float2uint_rz(__fmul_rz(mm_clamp01(
 // product exact inside the fma, i.e. the truncated double product of the reference -- one FP32 instruction, no conversion
 MM_DEV unsigned mm_quant_bits(float v) { return (unsigned)__float_as_int(__fmaf_rz(mm_clamp01(v), 255.0f, 8388608.0f)); }
 
-MM_DEV void mm_store_word(const mm_params &P, int row, int col, unsigned word) {  // out_mode 0 only
-    ((unsigned *)((char *)P.out + (size_t)(row - P.first_row) * (size_t)P.out_stride))[col] = word;
-}
-MM_DEV void mm_store_pixel(const mm_params &P, int row, int col, const mm_tup<4> &t) {
-    char *rowp = (char *)P.out + (size_t)(row - P.first_row) * (size_t)P.out_stride;
+// rowp: the output row of this pixel (P.out + compact row * P.out_stride)
+MM_DEV void mm_store_word(char *rowp, int col, unsigned word) { ((unsigned *)rowp)[col] = word; }  // out_mode 0 only
+MM_DEV void mm_store_pixel(const mm_params &P, char *rowp, int col, const mm_tup<4> &t) {
     if (P.out_mode == 0) {  // RGBA8
         const unsigned rg = __byte_perm(mm_quant_bits(t.v[0]), mm_quant_bits(t.v[1]), 0x0040);
         const unsigned ba = __byte_perm(mm_quant_bits(t.v[2]), mm_quant_bits(t.v[3]), 0x0040);

@@ -144,6 +144,37 @@ def test_full_size_mandelbrot_symmetry_and_band_agreement():
         assert torch.equal(buf[:n], out[idx])
 
 
+def test_rows_per_thread_and_interleaved_bands_agree():
+    """A straight-line filter renders four 32x8 tiles per block by default (mmb_set_rows_per_thread); every setting gives
+    the same frame, also for 8-row blocks interleaved over ranks with a ragged height, and for row bands."""
+    import torch
+    from mathmap_b200 import sharding
+    W, H = 640, 1003
+    img = synthetic_rgba(W, H)
+    m = mb.Module(source=filter_source("examples/Distorts/Twirl.mm"))
+    frames = []
+    for rows in (None, 1, 2, 4, 8):
+        inv = mb.Invocation(m, W, H, antialiasing=True, rows_per_thread=rows)
+        inv.set("in", img)
+        frames.append(inv.render(0, 0.3))
+        assert np.array_equal(frames[0], frames[-1]), "rows_per_thread=%r" % rows
+    want = OracleFilter(m.ir).render(W, H, {"in": img}, t=0.3, antialiasing=True, sample_rows=[0, 7, 8, 500, 1002])
+    assert np.array_equal(frames[0][[0, 7, 8, 500, 1002]], want)
+    inv = mb.Invocation(m, W, H, antialiasing=True)
+    inv.set("in", img)
+    inv.init_frame(0, 0.3)
+    whole = torch.from_numpy(frames[0]).cuda()
+    for world in (2, 3):
+        for r in range(world):
+            idx = sharding.interleaved_rows_for_rank(H, r, world)
+            buf = torch.zeros(((len(idx) + 7) // 8 * 8, W, 4), dtype=torch.uint8, device="cuda")
+            inv.calc_lines_interleaved_device(buf.data_ptr(), r, world)
+            inv.synchronize()
+            assert torch.equal(buf[:len(idx)], whole[torch.tensor(idx, device="cuda")]), "world %d rank %d" % (world, r)
+    parts = [inv.calc_lines(a, b) for a, b in ((0, 13), (13, 500), (500, 1003))]
+    assert np.array_equal(np.concatenate(parts, axis=0), frames[0])
+
+
 def test_full_size_ident_round_trip_and_twirl_rows():
     """8192x8192 synthetic input: Ident reproduces the input bit-exactly (nearest and bilinear);
     Twirl rows agree with the oracle."""
