@@ -843,11 +843,6 @@ mmb_invocation *mmb_invoke(mmb_module *m, int img_width, int img_height, int dev
         inv->device = device;
         inv->W = img_width;
         inv->H = img_height;
-        // tuning override for experiments (the API is mmb_set_rows_per_thread)
-        if (const char *e = getenv("MMB_ROWS_PER_THREAD")) {
-            int r = atoi(e);
-            if (r == 1 || r == 2 || r == 4 || r == 8) inv->cfg.rows = r;
-        }
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0)

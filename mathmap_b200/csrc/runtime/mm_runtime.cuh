@@ -587,6 +587,17 @@ MM_DEV mm_color mm_sample_bilinear(const mm_params &P, const mm_image &img, floa
 MM_DEV float mm_byte_as_float(unsigned word, unsigned magic, unsigned sel /* 0x7650 | byte index */) {
     return __fsub_rn(__int_as_float(__byte_perm(word, magic, sel)), 8388608.0f);
 }
+// Channel k of a texel as a float.  The PRMT + FADD pair costs two issue slots on the FP32/ALU pipes, the conversion
+// instruction (I2F.U8 with a byte selector) one slot but several cycles of the narrow XU pipe: the kernels are bound by
+// issue slots, so MM_XU_CHANNELS of the four channels go through the XU pipe.  Measured on Ident 8192^2 (bilinear) for
+// 0 / 1 / 2 / 3 / 4 channels: 0.313 / 0.309 / 0.299 / 0.295 / 0.303 ms (with all four the XU pipe starts to limit).
+#ifndef MM_XU_CHANNELS
+#define MM_XU_CHANNELS 3
+#endif
+MM_DEV float mm_texel_channel(unsigned word, unsigned magic, int k) {
+    if (k >= 4 - MM_XU_CHANNELS) return (float)((word >> (8 * k)) & 0xffu);
+    return mm_byte_as_float(word, magic, 0x7650u | (unsigned)k);
+}
 MM_DEV float mm_unit_from_rounded(float qf) {  // qf holds an integer 0..255 exactly
     return __fmaf_rn(qf, 0.003921568859368563f, __fmul_rn(qf, -2.319175823606301e-10f));
 }
@@ -616,9 +627,8 @@ template <bool WORD> MM_DEV bool mm_bilinear_interior(const mm_params &P, const 
     unsigned q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {  // memory byte k is R, G, B, A
-        const unsigned sel = 0x7650u | (unsigned)k;
-        const float a = mm_byte_as_float(t1, magic, sel), b = mm_byte_as_float(t2, magic, sel), c = mm_byte_as_float(t3, magic, sel),
-                    d = mm_byte_as_float(t4, magic, sel);
+        const float a = mm_texel_channel(t1, magic, k), b = mm_texel_channel(t2, magic, k), c = mm_texel_channel(t3, magic, k),
+                    d = mm_texel_channel(t4, magic, k);
         const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, p1), __fmul_rn(b, p2)), __fmul_rn(c, p3)), __fmul_rn(d, p4));
         const float biased = __fadd_rn(s, MM_MAGIC_ROUND);  // 1.5 * 2^23 + rintf(s), 0 <= s < 256: the low mantissa byte is (int)rintf(s) & 0xff
         if (WORD) q[k] = (unsigned)__float_as_int(biased);
@@ -658,7 +668,6 @@ template <bool WORD> MM_DEV bool mm_nearest_interior(const mm_params &P, const m
 // bilinear sampler the blend of four equal bytes c is c again: the float weights sum to 1 within 4 * 2^-24 and the
 // seven roundings add less than 2^-21 relative, so |s - c| < 3e-4 and rintf(s) = c (tests/test_cabi.py checks the bound).  Filters that recurse until a
 // tap lands inside the picture (Droste) take this path for most of their taps.  NaN coordinates fail every test.
-MM_DEV mm_tup<4> mm_tuple_from_edge(mm_color c) { return mm_tuple_from_color(c); }
 MM_DEV bool mm_bilinear_exterior(const mm_params &P, const mm_image &img, float x, float y, mm_color &edge) {
 #if MM_EDGE_X == 0 && MM_EDGE_Y == 0
     if (!(img.fast_w > 0.0f)) return false;
@@ -713,13 +722,13 @@ MM_DEV mm_tup<4> mm_orig_val(const mm_params &P, int image, float x, float y, fl
     unsigned unused;
     if (mm_bilinear_interior<false>(P, img, x, y, t, r, unused)) return r;
     mm_color edge;
-    if (mm_bilinear_exterior(P, img, x, y, edge)) return mm_tuple_from_edge(edge);
+    if (mm_bilinear_exterior(P, img, x, y, edge)) return mm_tuple_from_color(edge);
     return mm_tuple_from_color(mm_sample_bilinear(P, img, x, y, mm_f2i(t)));
 #else
     unsigned unused;
     if (mm_nearest_interior<false>(P, img, x, y, t, r, unused)) return r;
     mm_color edge;
-    if (mm_nearest_exterior(P, img, x, y, edge)) return mm_tuple_from_edge(edge);
+    if (mm_nearest_exterior(P, img, x, y, edge)) return mm_tuple_from_color(edge);
     return mm_tuple_from_color(mm_sample_nearest(P, img, x, y, mm_f2i(t)));
 #endif
 }
