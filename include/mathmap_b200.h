@@ -71,7 +71,7 @@ int mmb_set_supersampling(mmb_invocation *inv, int enabled);  /* invocation->sup
 int mmb_set_edge_behaviour(mmb_invocation *inv, int mode_x, int mode_y, uint32_t color_x, uint32_t color_y);
 int mmb_set_output_bpp(mmb_invocation *inv, int bpp);         /* invocation->output_bpp: 1, 2, 3 or 4 */
 int mmb_set_warp_shape(mmb_invocation *inv, int warp_width); /* pixels per warp row in the 32x8 tile: 32 (default), 16 or 8 */
-int mmb_set_rows_per_thread(mmb_invocation *inv, int rows); /* 32x8 tiles one block renders in sequence (1, 2, 4 or 8; 0 = automatic, the default: 4 for straight-line pixel code, 1 for loops) */
+int mmb_set_rows_per_thread(mmb_invocation *inv, int rows); /* 32x8 tiles one block renders in sequence (1, 2, 4 or 8; 0 = automatic, the default: up to 8 for straight-line pixel code on large grids, 1 for per-pixel loops, which ignore the setting) */
 int mmb_set_precise_math(mmb_invocation *inv, int enabled);   /* 1 (default): libm calls evaluated in double and narrowed, like the host; 0: CUDA float libm (<= 2 ulp, faster) */
 
 /* userval bindings, reference userval.h userval_t / mathmap_cmdline.c:756-796 (-D name=value) */

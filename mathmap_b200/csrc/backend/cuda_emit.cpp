@@ -644,6 +644,7 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         if (have_rows) k.row_kernel_name = "mm_rows_" + name;
         // Straight-line pixel code gains from rendering several tiles per block (the per-column work and the constant
         // loads are shared); loops (escape-time iteration, Droste levels) make tiles uneven and measured slower that way.
+        // auto_rows is the most tiles a block of this kernel takes; the launch picks fewer for small grids.
         {
             std::function<bool(const Stmt *)> has_loop = [&](const Stmt *st) {
                 for (; st; st = st->next) {
@@ -652,7 +653,7 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
                 }
                 return false;
             };
-            k.auto_rows = has_loop(code->first) ? 1 : 4;
+            k.auto_rows = has_loop(code->first) ? 1 : 8;
         }
 
         std::ostringstream fn;
@@ -672,7 +673,7 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H) " << k.kernel_name << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
            << name << " U, const __grid_constant__ mm_rowvals_" << name << " RV) {\n"
            << "    int col, mm_row0;\n"
-           << "    constexpr int mm_rows = MM_ROWS ? MM_ROWS : " << k.auto_rows << ";\n"
+           << (k.auto_rows > 1 ? "    const int mm_rows = P.rows;\n" : "    constexpr int mm_rows = 1;  // per-pixel loops: one tile per block\n")
            << "    mm_pixel_coords(col, mm_row0, mm_rows);\n"
            << "    if (col >= P.region_w) return;\n"
            << "    const float x = __ldg(P.xs + (col + P.region_x));\n"

@@ -30,7 +30,7 @@ struct FilterKernel {
     int row_slots = 0;
     int filter_index = -1;             // position in the module's filter list: mm_image::closure_filter of its closures
     bool closure_fn = false;           // a device function mm_closure_<f> exists (the filter occurs as a closure value)
-    int auto_rows = 1;                 // 32x8 tiles a block renders in sequence unless the configuration says otherwise (MM_ROWS != 0)
+    int auto_rows = 1;                 // the most 32x8 tiles a block renders in sequence (1 for kernels with per-pixel loops)
 };
 
 struct CudaModuleSource {

@@ -570,7 +570,19 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     void *params[3] = {&P, (void *)fd.uniforms.data(), (void *)rowvals.data()};
     unsigned gx = (unsigned)((g.region_w + 31) / 32), gy;
     {
-        const int rows = inv->cfg.rows ? inv->cfg.rows : k.auto_rows;
+        // Tiles per block: as many as the kernel takes (k.auto_rows) while the grid still has about six waves of
+        // blocks (8 resident blocks per SM), so that the tail of a small frame stays short.  Measured at 8192^2 for
+        // 4 -> 8 tiles: Ident 0.295 -> 0.283 ms, Invert 0.255 -> 0.235 ms; at 3840x2160 (Sea): 11.7 -> 12.6 ms.
+        int rows = k.auto_rows > 1 ? inv->cfg.rows : 1;  // kernels with per-pixel loops are compiled for one tile per block
+        if (rows == 0) {
+            static int sm_count[64];  // per device ordinal, 0 = not asked yet
+            int &sms = sm_count[inv->device & 63];
+            if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, inv->device) != cudaSuccess) sms = 148;
+            const long long want = 6ll * 8 * sms;
+            rows = k.auto_rows;
+            while (rows > 1 && (long long)gx * ((g.num_rows + 8 * rows - 1) / (8 * rows)) < want) rows /= 2;
+        }
+        P.rows = rows;
         gy = (unsigned)((g.num_rows + 8 * rows - 1) / (8 * rows));
     }
     if (gx == 0 || gy == 0) return;

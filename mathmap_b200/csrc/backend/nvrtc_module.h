@@ -16,7 +16,8 @@ namespace mmbackend {
 void set_error(const std::string &msg);
 
 struct KernelConfig {
-    int aa = 0, supersampling = 0, edge_x = 0, edge_y = 0, precise = 1, warp_w = 32, rows = 0;  // rows: 32x8 tiles a block renders in sequence, 0 = the emitter's choice per kernel
+    int aa = 0, supersampling = 0, edge_x = 0, edge_y = 0, precise = 1, warp_w = 32;
+    int rows = 0;  // 32x8 tiles a block renders in sequence (a launch parameter, not part of the key); 0 = chosen per launch
     std::string key() const;
 };
 

@@ -47,12 +47,9 @@
 #endif
 #define MM_BLOCK_W 32
 #define MM_BLOCK_H 8
-// MM_ROWS: a block renders MM_ROWS vertically adjacent tiles one after the other (row, row + 8, ...), so that what
-// depends on the column only (coordinate load and scaling, constant loads) is done once per thread.
-// MM_ROWS 0: each kernel uses the count the emitter chose for it.
-#ifndef MM_ROWS
-#define MM_ROWS 0
-#endif
+// A block renders `rows` (mm_params::rows, chosen per launch) vertically adjacent tiles one after the other (row,
+// row + 8, ...), so that what depends on the column only (coordinate load and scaling, constant loads) is done once
+// per thread.
 MM_DEV void mm_pixel_coords(int &col, int &row, int rows) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #if MM_WARP_W == 32
@@ -655,7 +652,7 @@ template <bool WORD> MM_DEV bool mm_nearest_interior(const mm_params &P, const m
     if (WORD) { word = texel; return true; }
     const unsigned magic = P.magic23;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out.v[k] = mm_unit_from_rounded(mm_byte_as_float(texel, magic, 0x7650u | (unsigned)k));
+    for (int k = 0; k < 4; ++k) out.v[k] = mm_unit_from_rounded(mm_texel_channel(texel, magic, k));
     return true;
 #else
     return false;

@@ -38,6 +38,7 @@ struct mm_params {
     int first_row, num_rows;  // band, in absolute rows (num_rows counts rendered rows)
     int row_limit;            // absolute row bound (exclusive)
     int row_interleave, row_phase;  // > 1: render only 8-row blocks b with b % row_interleave == row_phase, stored compactly
+    int rows;                 // 32x8 tiles a block renders in sequence (grid.y = ceil(num_rows / (8 * rows)))
     int img_w, img_h, render_w, render_h;
     int frame;
     float t;

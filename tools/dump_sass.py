@@ -1,5 +1,5 @@
 """Compiles a filter's generated CUDA (as NVRTC would) with nvcc to a cubin and prints the SASS of its pixel kernel.
-Usage: python tools/dump_sass.py FILTER.mm [aa=1] [precise=1] [rows=1] > out.sass"""
+Usage: python tools/dump_sass.py FILTER.mm [aa=1] [precise=1] > out.sass"""
 import os, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -7,8 +7,7 @@ import mathmap_b200 as mb
 m = mb.Module.from_file(sys.argv[1])
 aa = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 precise = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-rows = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-src = m.cuda_source.replace("#define MM_AA 0", "#define MM_AA %d" % aa).replace("#define MM_PRECISE 1", "#define MM_PRECISE %d" % precise).replace("#define MM_ROWS 0", "#define MM_ROWS %d" % rows)
+src = m.cuda_source.replace("#define MM_AA 0", "#define MM_AA %d" % aa).replace("#define MM_PRECISE 1", "#define MM_PRECISE %d" % precise)
 d = tempfile.mkdtemp()
 open(os.path.join(d, "k.cu"), "w").write(src)
 rt = os.path.join(ROOT, "mathmap_b200", "csrc", "runtime")
