@@ -1,0 +1,41 @@
+"""Host-side checks of the CUDA emitter's structural decisions (no GPU needed: the generated source is inspected)."""
+import os
+
+import mathmap_b200 as mb
+
+FILTERS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "filters", "examples")
+
+
+def source_of(rel=None, text=None):
+    m = mb.Module.from_file(os.path.join(FILTERS, rel)) if rel else mb.Module(source=text)
+    return m.cuda_source
+
+
+def test_direct_output_only_when_the_pixel_is_the_sample():
+    # every distortion filter ends in in(...): the sampler may hand its bytes to the store (mm_orig_val_out)
+    for rel in ("Distorts/Twirl.mm", "Distorts/Sea.mm", "Utilities/Ident.mm", "Geometry/Zoom.mm"):
+        src = source_of(rel)
+        assert "mm_orig_val_out(" in src and "mm_store_word(" in src, rel
+    # a sample that is post-processed, used twice, or produced inside a conditional keeps the general path
+    post = "filter f (image in)\n  c = in(xy);\n  rgba:[1-c[0], c[1], c[2], c[3]]\nend\n"
+    twice = "filter g (image in)\n  c = in(xy);\n  d = c[0];\n  if d > 0.5 then c else rgba:[d, d, d, 1] end\nend\n"
+    for text in (post, twice):
+        src = source_of(text=text)
+        assert "mm_orig_val_out(" not in src and "mm_store_word(" not in src
+    assert "mm_orig_val_out(" not in source_of("Render/Mandelbrot.mm")
+
+
+def test_tiles_per_block_follow_the_kernel_shape():
+    # straight-line pixel code takes the tile count from the launch parameters; per-pixel loops are compiled for one tile
+    assert "const int mm_rows = P.rows;" in source_of("Distorts/Twirl.mm")
+    assert "const int mm_rows = P.rows;" in source_of("Colors/Invert.mm")
+    for rel in ("Render/Mandelbrot.mm", "Map/Droste.mm"):
+        src = source_of(rel)
+        assert "constexpr int mm_rows = 1;" in src and "P.rows" not in src, rel
+
+
+def test_pow_2_is_an_exact_product():
+    src = source_of(text="filter h ()\n  v = x^2 + y^2;\n  grayColor(v)\nend\n")
+    assert "mm_sqr(" in src and "mm_pow(" not in src
+    src = source_of(text="filter k ()\n  grayColor(abs(x)^2.5)\nend\n")
+    assert "mm_pow(" in src
