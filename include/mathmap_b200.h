@@ -122,6 +122,10 @@ int mmb_gaussian_blur_device(int device, const float *device_in, float *device_o
 
 /* NVRTC-compiles the module for sm_100a without needing a GPU (build check); returns cubin bytes or -1 */
 long mmb_module_compile_check(mmb_module *m, int antialiasing, int precise_math);
+/* Optional persistent cubin cache, process-wide: with a directory set, compiled kernels are stored there under a key of the
+ * NVRTC version, options, device runtime and generated source, and loaded instead of recompiled by later processes.  The
+ * reference has no equivalent (gcc runs on every load of a filter, backends/cc.c:634-758).  NULL or "" turns it off (default). */
+int mmb_set_cubin_cache_dir(const char *dir);
 /* the IIR coefficients the blur computes on the host: 30 doubles n_p n_m d_p d_m bd_p bd_m (gauss.c:39-115) */
 void mmb_gauss_iir_constants(float std_dev, double *out30);
 const char *mmb_last_error(void);

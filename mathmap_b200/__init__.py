@@ -43,7 +43,7 @@ def lib():
         "mmb_module_num_uservals": (ci, [vp]),
         "mmb_module_userval_info": (ci, [vp, ci, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ci), ctypes.POINTER(cf), ctypes.POINTER(cf), ctypes.POINTER(cf)]),
         "mmb_module_userval_index": (ci, [vp, cc]),
-        "mmb_module_compile_check": (ctypes.c_long, [vp, ci, ci]),
+        "mmb_module_compile_check": (ctypes.c_long, [vp, ci, ci]), "mmb_set_cubin_cache_dir": (ci, [ctypes.c_char_p]),
         "mmb_invoke": (vp, [vp, ci, ci, ci]), "mmb_invocation_free": (None, [vp]),
         "mmb_set_antialiasing": (ci, [vp, ci]), "mmb_set_supersampling": (ci, [vp, ci]),
         "mmb_set_edge_behaviour": (ci, [vp, ci, ci, ctypes.c_uint32, ctypes.c_uint32]),
@@ -71,6 +71,11 @@ def lib():
 
 def _err():
     return lib().mmb_last_error().decode("utf-8", "replace")
+
+
+def set_cubin_cache_dir(path):
+    """Opt-in persistent cache of compiled kernels (None turns it off); see mmb_set_cubin_cache_dir."""
+    lib().mmb_set_cubin_cache_dir(None if not path else os.fsencode(path))
 
 
 def design_to_source(design_text, filter_path):

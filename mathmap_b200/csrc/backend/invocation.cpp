@@ -836,6 +836,11 @@ const char *mmb_module_cuda_source(mmb_module *m) {
 }
 
 // Build check without a GPU: NVRTC-compiles the module for sm_100a; returns cubin bytes or -1.
+int mmb_set_cubin_cache_dir(const char *dir) {
+    set_cubin_cache_dir(dir);
+    return 0;
+}
+
 long mmb_module_compile_check(mmb_module *m, int antialiasing, int precise_math) {
     if (!m) return -1;
     KernelConfig cfg;

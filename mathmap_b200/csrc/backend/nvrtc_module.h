@@ -59,6 +59,8 @@ struct ModuleBackend {
     double last_compile_ms = 0.0;
 };
 
+void set_cubin_cache_dir(const char *dir);  // NULL or "": no persistent cache (the default)
+
 std::shared_ptr<ModuleBackend> get_module_backend(mmb_module *m);  // creates on first use; throws mm::CompileError
 
 }  // namespace mmbackend

@@ -98,3 +98,33 @@ def test_bilinear_blend_of_equal_bytes_returns_the_byte():
         cf = f32(c)
         s = ((cf * p1 + cf * p2).astype(f32) + cf * p3).astype(f32) + cf * p4
         assert (np.rint(s.astype(f32)) == c).all()
+
+
+def test_persistent_cubin_cache(tmp_path):
+    """mmb_set_cubin_cache_dir: the first compile of a configuration writes DIR/<key>.cubin, later ones (a new module,
+    as in a new process) load it instead of running NVRTC; another configuration gets another file."""
+    import time
+    src = open(os.path.join(ROOT, "tests", "golden", "filters", "examples", "Distorts", "Twirl.mm")).read()
+    plain = mb.Module(source=src).compile_check(antialiasing=True, precise=True)
+    mb.set_cubin_cache_dir(str(tmp_path))
+    try:
+        t0 = time.perf_counter()
+        first = mb.Module(source=src).compile_check(antialiasing=True, precise=True)
+        t_first = time.perf_counter() - t0
+        files = sorted(os.listdir(tmp_path))
+        assert len(files) == 1 and files[0].endswith(".cubin") and len(files[0]) == 32 + 6
+        assert os.path.getsize(os.path.join(tmp_path, files[0])) == first + 24
+        t0 = time.perf_counter()
+        second = mb.Module(source=src).compile_check(antialiasing=True, precise=True)
+        t_second = time.perf_counter() - t0
+        assert first == second == plain
+        assert t_second < t_first / 3, (t_first, t_second)
+        mb.Module(source=src).compile_check(antialiasing=False, precise=True)
+        assert len(os.listdir(tmp_path)) == 2
+        # a damaged file is ignored and replaced
+        path = os.path.join(tmp_path, files[0])
+        open(path, "wb").write(b"garbage")
+        assert mb.Module(source=src).compile_check(antialiasing=True, precise=True) == plain
+        assert os.path.getsize(path) == plain + 24
+    finally:
+        mb.set_cubin_cache_dir(None)
