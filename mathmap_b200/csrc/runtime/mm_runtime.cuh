@@ -571,12 +571,14 @@ MM_DEV mm_color mm_sample_bilinear(const mm_params &P, const mm_image &img, floa
 
 // ---- interior fast paths -------------------------------------------------------
 // When every texel a sample touches lies inside the image (the common case) the
-// generic path's per-texel edge handling, 64-bit addressing and int<->float
-// conversions (I2F/F2I issue on the quarter-rate XU pipe) are replaced by:
+// generic path's per-texel edge handling, 64-bit addressing and chains of
+// int<->float conversions (FRND, F2I, I2F on the narrow XU pipe) are replaced by:
 //   * one float range test per axis (NaN and out-of-range fall to the generic path),
-//   * byte -> float through PRMT into the mantissa of 2^23 (exact),
+//   * floor and the texel index from one round-down add of 2^23 (mm_floor_biased),
+//   * byte -> float through PRMT into the mantissa of 2^23 (exact) for one channel and through I2F.U8 for the other
+//     three, which balances issue slots against the XU pipe (mm_texel_channel),
 //   * rintf + (int) through the 1.5 * 2^23 magic constant (round half to even, exact for 0..255),
-//   * byte/255 from the rounded float directly.
+//   * byte/255 from the rounded float directly -- or, when the sample is the pixel (WORD), the rounded bytes themselves.
 // Results are bit-identical to the generic path.
 #define MM_MAGIC_ROUND 12582912.0f  /* 1.5 * 2^23 */
 // `magic` is 0x4B000000 read from mm_params: as a literal the compiler would keep it as PRMT's immediate and spend a
