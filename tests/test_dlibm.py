@@ -1,7 +1,8 @@
 """mathmap_b200/csrc/runtime/mm_dlibm.h evaluates sin, cos, asin, acos, atan, atan2, exp and log of float arguments in double with its own
 polynomials (coefficients in constant memory) and narrows to float.  The reference computes RN_float(libm(x)) with the
 host's double libm (ops.lisp:126-147); this compiles the header for the host and compares the two on a prime-stride
-sample of all float bit patterns (the full sweep, stride 1, has no mismatch either: 4.3e9 arguments)."""
+sample of all float bit patterns (the full sweep, stride 1: no mismatch for sin, cos, acos, atan, exp and log; asin differs by one
+float ulp for 2 of 2.1e9 arguments, atan2 for 2 of 8.6e9 pairs)."""
 import os
 import subprocess
 
