@@ -11,6 +11,14 @@ import sys
 def rows_of(report):
     out = subprocess.run(["ncu", "-i", report, "--page", "source", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
+    # one section per profiled kernel ("Kernel Name" row, header row, instructions); MMB_NCU_KERNEL picks one (default 0)
+    import os
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    sections = [(starts[i], starts[i + 1]) for i in range(len(starts) - 1)]
+    sections = sections[::2] if len(sections) > 1 and rows[sections[0][0]] == rows[sections[1][0]] else sections  # ncu lists every kernel twice
+    k = int(os.environ.get("MMB_NCU_KERNEL", "0"))
+    rows = rows[sections[k][0]:sections[k][1]]
+    print("kernel:", rows[0][1] if len(rows[0]) > 1 else "?")
     hdr = rows[1]
     col = {name: hdr.index(name) for name in ("Address", "Source", "Instructions Executed", "# Samples", "stall_long_sb", "stall_wait")}
     body = [r for r in rows[2:] if len(r) > col["# Samples"] and r[col["Instructions Executed"]].isdigit()]
