@@ -1,4 +1,5 @@
 """Front end and IR: language rules that decide what a filter means, IR text round trip, constness levels.  CPU only."""
+import os
 import re
 
 import pytest
@@ -105,3 +106,12 @@ def test_computed_subscripts_become_tree_vectors():
     # the IR text round-trips through the loader
     m2 = mb.Module(ir=ir)
     assert m2.ir == ir
+
+
+def test_committed_workload_ir_is_what_the_front_end_produces():
+    """tests/golden/ir/*.mmir (tools/make_golden_ir.py) feed the oracle in bench.py's CPU legs without loading the CUDA
+    library; they must not drift from the front end."""
+    import bench
+    for name, wl in bench.WORKLOADS.items():
+        m = mb.Module.from_file(os.path.join(bench.FILTERS, wl["script"]))
+        assert m.ir == bench.workload_ir(name), "%s: run tools/make_golden_ir.py" % name
