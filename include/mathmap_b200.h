@@ -70,6 +70,10 @@ int mmb_set_antialiasing(mmb_invocation *inv, int enabled);   /* invocation_set_
 int mmb_set_supersampling(mmb_invocation *inv, int enabled);  /* invocation->supersampling (-o flag) */
 int mmb_set_edge_behaviour(mmb_invocation *inv, int mode_x, int mode_y, uint32_t color_x, uint32_t color_y);
 int mmb_set_output_bpp(mmb_invocation *inv, int bpp);         /* invocation->output_bpp: 1, 2, 3 or 4 */
+/* invocation->render_width / render_height (mathmap.h:180-181) when they differ from the image size: the GIMP preview
+ * renders a scaled frame (mathmap.c:2191-2223).  __renderPixelW/H read them and native filters render their
+ * intermediates at this size (native-filters/gauss.c:657, convolve.c:88).  Default: the image size. */
+int mmb_set_render_size(mmb_invocation *inv, int render_width, int render_height);
 int mmb_set_warp_shape(mmb_invocation *inv, int warp_width); /* pixels per warp row in the 32x8 tile: 32 (default), 16 or 8 */
 int mmb_set_rows_per_thread(mmb_invocation *inv, int rows); /* 32x8 tiles one block renders in sequence (1, 2, 4 or 8; 0 = automatic, the default: up to 8 for straight-line pixel code on large grids, 1 for per-pixel loops, which ignore the setting) */
 int mmb_set_precise_math(mmb_invocation *inv, int enabled);   /* 1 (default): libm calls evaluated in double and narrowed, like the host; 0: CUDA float libm (<= 2 ulp, faster) */
@@ -79,6 +83,7 @@ int mmb_set_userval_int(mmb_invocation *inv, int index, int value);
 int mmb_set_userval_float(mmb_invocation *inv, int index, float value);
 int mmb_set_userval_bool(mmb_invocation *inv, int index, int value);
 int mmb_set_userval_color(mmb_invocation *inv, int index, float r, float g, float b, float a);
+int mmb_set_userval_color_packed(mmb_invocation *inv, int index, uint32_t rgba_packed); /* userval_t.v.color.value as it is: R in the high byte (color.h:36-43) */
 int mmb_set_userval_curve(mmb_invocation *inv, int index, const float *values /* MMB_CURVE_POINTS */);
 int mmb_set_userval_gradient(mmb_invocation *inv, int index, const uint32_t *rgba_packed /* MMB_CURVE_POINTS, R in the high byte */);
 /* input drawables are RGBA8, rows top to bottom, R first (color.h:36-43 packing is applied on load).
@@ -101,6 +106,31 @@ int mmb_set_userval_image_device(mmb_invocation *inv, int index, const void *dev
 int mmb_init_frame(mmb_invocation *inv, int frame, float t);
 int mmb_calc_lines(mmb_invocation *inv, int first_row, int last_row, void *q, int floatmap);
 int mmb_calc_lines_device(mmb_invocation *inv, int first_row, int last_row, void *device_q, int floatmap, void *stream);
+
+/* mmb_calc_lines_slice IS mathfuncs_t.calc_lines (compiler.h:50-56): `void calc_lines(mathmap_slice_t *slice, image_t
+ * *closure, int first_row, int last_row, void *q, int floatmap)` with every parameter the reference's generated
+ * calc_lines_<f> reads from its slice, frame and invocation (new_template.c.in:208-312):
+ *   frame_render_width/height ... mathmap_frame_t (mathmap.h:207-219): the frame the virtual coordinates refer to
+ *   region_x/y/width/height ..... mathmap_slice_t (mathmap.h:221-230): the rectangle of that frame this call covers;
+ *                                 GIMP hands over tile-sized regions with region_x != 0 (mathmap.c:1160-1175)
+ *   sampling_offset_x/y ......... mathmap_slice_t: 0, or -0.5 for the one-column-wider slice of supersampling
+ *   row_stride .................. invocation->row_stride in bytes (mathmap.c:1168 sets the GIMP region's rowstride);
+ *                                 floatmap output advances by frame_render_width float[4] pixels instead
+ * Rows [max(0, first_row), min(last_row, region_y + region_height)) are rendered (absolute frame rows); q points at the
+ * first rendered row, pixel (region_x + c) of a row at q + c * output_bpp.  No supersampling combine happens here: the
+ * reference's caller does it with three calls per row (call_invocation, mathmap_common.c:880-927); mmb_set_supersampling
+ * only selects the nearest sampler's missing +0.5 (builtins.c:155-159) like invocation->supersampling.
+ * mmb_calc_lines above is the whole call_invocation for a full-width band, supersampling included. */
+typedef struct mmb_slice {
+    int frame_render_width, frame_render_height;
+    int region_x, region_y, region_width, region_height;
+    float sampling_offset_x, sampling_offset_y;
+    int row_stride;
+} mmb_slice;
+int mmb_calc_lines_slice(mmb_invocation *inv, const mmb_slice *slice, int first_row, int last_row, void *q, int floatmap);
+/* the same into device memory, asynchronously on `stream` (0 = the library's stream, the legacy default stream) */
+int mmb_calc_lines_slice_device(mmb_invocation *inv, const mmb_slice *slice, int first_row, int last_row, void *device_q, int floatmap,
+                                void *stream);
 /* Row-band sharding across GPUs with load balance (the reference splits one frame into contiguous bands per
  * thread, mathmap_common.c:991-1003; escape-time filters make contiguous bands unequal): renders the 8-row
  * blocks b with b % count == phase into device_q, compactly (this rank's k-th block at rows [8k, 8k+8)). */

@@ -27,6 +27,13 @@ class MathMapError(RuntimeError):
     pass
 
 
+class Slice(ctypes.Structure):
+    """mmb_slice: what the reference's calc_lines reads from mathmap_slice_t / mathmap_frame_t / invocation->row_stride."""
+    _fields_ = [("frame_render_width", ctypes.c_int), ("frame_render_height", ctypes.c_int),
+                ("region_x", ctypes.c_int), ("region_y", ctypes.c_int), ("region_width", ctypes.c_int), ("region_height", ctypes.c_int),
+                ("sampling_offset_x", ctypes.c_float), ("sampling_offset_y", ctypes.c_float), ("row_stride", ctypes.c_int)]
+
+
 def lib():
     """Loads libmathmap_b200.so (built in-tree by mathmap_b200.build); fails loudly if it is missing."""
     global _lib
@@ -50,10 +57,13 @@ def lib():
         "mmb_set_output_bpp": (ci, [vp, ci]), "mmb_set_precise_math": (ci, [vp, ci]), "mmb_set_warp_shape": (ci, [vp, ci]), "mmb_set_rows_per_thread": (ci, [vp, ci]),
         "mmb_set_userval_int": (ci, [vp, ci, ci]), "mmb_set_userval_float": (ci, [vp, ci, cf]), "mmb_set_userval_bool": (ci, [vp, ci, ci]),
         "mmb_set_userval_color": (ci, [vp, ci, cf, cf, cf, cf]),
+        "mmb_set_userval_color_packed": (ci, [vp, ci, ctypes.c_uint32]),
         "mmb_set_userval_curve": (ci, [vp, ci, vp]), "mmb_set_userval_gradient": (ci, [vp, ci, vp]),
         "mmb_set_userval_image_host": (ci, [vp, ci, vp, ci, ci]), "mmb_set_userval_image_device": (ci, [vp, ci, vp, ci, ci]),
         "mmb_init_frame": (ci, [vp, ci, cf]),
         "mmb_calc_lines": (ci, [vp, ci, ci, vp, ci]), "mmb_calc_lines_device": (ci, [vp, ci, ci, vp, ci, vp]),
+        "mmb_calc_lines_slice": (ci, [vp, vp, ci, ci, vp, ci]), "mmb_calc_lines_slice_device": (ci, [vp, vp, ci, ci, vp, ci, vp]),
+        "mmb_set_render_size": (ci, [vp, ci, ci]),
         "mmb_render_frames_device": (ci, [vp, ci, vp, vp, vp, vp]),
         "mmb_calc_lines_interleaved_device": (ci, [vp, ci, ci, vp, vp]),
         "mmb_synchronize": (ci, [vp]), "mmb_launch_count": (ctypes.c_long, [vp]), "mmb_kernel_name": (cc, [vp]),
@@ -88,6 +98,16 @@ def design_to_source(design_text, filter_path):
         return ctypes.string_at(p).decode()
     finally:
         L.mmb_free_string(p)
+
+
+def _check_out(out, need_bytes, dtype=None):
+    """The C ABI writes need_bytes at out's address: refuse anything but a large enough, writable, C-contiguous array."""
+    if not isinstance(out, np.ndarray) or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+        raise ValueError("out must be a writable C-contiguous numpy array")
+    if dtype is not None and out.dtype != dtype:
+        raise ValueError("out must be of dtype %s" % np.dtype(dtype).name)
+    if out.nbytes < need_bytes:
+        raise ValueError("out holds %d bytes, the call writes %d" % (out.nbytes, need_bytes))
 
 
 class Module:
@@ -232,7 +252,29 @@ class Invocation:
         rows = max(0, min(last_row, self.height) - max(0, first_row))
         if out is None:
             out = np.empty((rows, self.width, 4), dtype=np.float32) if floatmap else np.empty((rows, self.width, self.bpp), dtype=np.uint8)
+        else:
+            _check_out(out, rows * self.width * (16 if floatmap else self.bpp), np.float32 if floatmap else np.uint8)
         self._ck(lib().mmb_calc_lines(self._h, first_row, last_row, out.ctypes.data, int(floatmap)))
+        return out
+
+    def set_render_size(self, render_width, render_height):
+        self._ck(lib().mmb_set_render_size(self._h, render_width, render_height))
+
+    def calc_lines_slice(self, first_row, last_row, out, region=None, offset=(0.0, 0.0), frame_size=None, row_stride=None, floatmap=False):
+        """mathfuncs_t.calc_lines with the reference's slice parameters (mmb_calc_lines_slice): region = (x, y, w, h) of the
+        frame_size = (w, h) frame; `out` is a C-contiguous numpy buffer whose first byte is the first rendered row."""
+        fw, fh = frame_size or (self.width, self.height)
+        rx, ry, rw, rh = region or (0, 0, fw, fh)
+        if row_stride is None:
+            row_stride = rw * self.bpp
+        fr, lr = max(0, first_row), min(last_row, ry + rh)
+        need = 0
+        if lr > fr and rw > 0:
+            pitch = fw * 16 if floatmap else row_stride
+            need = (lr - fr - 1) * pitch + rw * (16 if floatmap else self.bpp)
+        _check_out(out, need)
+        sl = Slice(fw, fh, rx, ry, rw, rh, offset[0], offset[1], row_stride)
+        self._ck(lib().mmb_calc_lines_slice(self._h, ctypes.byref(sl), first_row, last_row, out.ctypes.data, int(floatmap)))
         return out
 
     def calc_lines_device(self, device_ptr, first_row=0, last_row=None, floatmap=False, stream=0):

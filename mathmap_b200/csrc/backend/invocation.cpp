@@ -90,7 +90,8 @@ struct mmb_invocation {
     mmb_module *m = nullptr;
     std::shared_ptr<ModuleBackend> backend;
     int device = 0;
-    int W = 0, H = 0;
+    int W = 0, H = 0;                // invocation->img_width / img_height
+    int render_w = 0, render_h = 0;  // invocation->render_width / render_height (differ from W, H in a scaled preview)
     KernelConfig cfg;
     uint32_t edge_color_x = 0, edge_color_y = 0;
     int bpp = 4;
@@ -116,9 +117,15 @@ struct mmb_invocation {
     cudaStream_t copy_stream = nullptr;  // device->host copies overlap the next chunk's kernel
     cudaStream_t aux_stream = nullptr;   // odd chunks render here so one chunk's tail overlaps the next chunk's head
     cudaEvent_t order_event = nullptr;   // start of a chunked band (timed)
+    // Ordering between the library's own stream (init_frame's renders, blurs and uploads) and a stream the caller
+    // passes to the *_device entry points: the caller's stream waits for `init_event`, recorded on the library's
+    // stream before the launch; what the library does next (recycling pool blocks, overwriting images) waits for
+    // `user_event`, recorded on the caller's stream after the launch.
+    cudaEvent_t init_event = nullptr, user_event = nullptr;
+    bool user_event_pending = false;
     // cost of each chunk of the last chunked band (ms between consecutive completions) and the band it belongs to
     std::vector<float> chunk_cost;
-    int cost_fr = -1, cost_lr = -1, cost_chunk_rows = -1, cost_floatmap = -1;
+    int cost_fr = -1, cost_lr = -1, cost_chunk_rows = -1, cost_floatmap = -1, cost_width = -1;
     std::vector<cudaEvent_t> chunk_events;
 
     void *alloc(size_t bytes) {
@@ -262,8 +269,8 @@ struct Replay {
             else if (n == "frame") { v.type = T_INT; v.i = frame; }
             else if (n == "__canvasPixelW") { v.type = T_INT; v.i = inv->W; }
             else if (n == "__canvasPixelH") { v.type = T_INT; v.i = inv->H; }
-            else if (n == "__renderPixelW") { v.type = T_INT; v.i = inv->W; }
-            else if (n == "__renderPixelH") { v.type = T_INT; v.i = inv->H; }
+            else if (n == "__renderPixelW") { v.type = T_INT; v.i = inv->render_w; }
+            else if (n == "__renderPixelH") { v.type = T_INT; v.i = inv->render_h; }
             else fail("internal " + n + " is not frame-constant");
             return v;
         }
@@ -554,7 +561,7 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     P.row_interleave = g.interleave;
     P.row_phase = g.phase;
     P.row_limit = g.row_limit >= 0 ? g.row_limit : g.first_row + g.num_rows;
-    P.img_w = inv->W; P.img_h = inv->H; P.render_w = inv->W; P.render_h = inv->H;
+    P.img_w = inv->W; P.img_h = inv->H; P.render_w = inv->render_w; P.render_h = inv->render_h;
     P.frame = frame;
     P.t = t;
     P.R = (float)sqrt(2.0);
@@ -662,7 +669,7 @@ int Replay::fft_native(const std::string &name, const std::vector<HVal> &args) {
     auto it = inv->native_cache.find(key);
     if (it != inv->native_cache.end()) return it->second;
     int in = args[0].image;
-    if (inv->images.at(in).kind != IMG_FLOATMAP) in = render_image(in, inv->W, inv->H, true);
+    if (inv->images.at(in).kind != IMG_FLOATMAP) in = render_image(in, inv->render_w, inv->render_h, true);  // convolve.c:88
     HostImage src = inv->images.at(in);
     HostImage out;
     out.kind = IMG_FLOATMAP;
@@ -708,7 +715,7 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
     // identity on texels, else a resampled RGBA8 copy) and converts on load; results are the same floats.
     const HostImage in_img = inv->images.at(in);
     if (in_img.kind == IMG_DRAWABLE) {
-        const int w = inv->W, hgt = inv->H;
+        const int w = inv->render_w, hgt = inv->render_h;  // gauss.c:657
         const float ax = (float)((float)(w - 1) / 2.0), ay = (float)((float)(hgt - 1) / 2.0) * -1.0f;  // floatmap_alloc, floatmap.c:30-47
         const float bx = ax, by = (float)((float)(hgt - 1) / 2.0);
         const float sh = (float)fabs((double)(h * ax)), sv = (float)fabs((double)(v * ay));
@@ -738,7 +745,7 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
         }
     }
     int fm = in;
-    if (inv->images.at(in).kind != IMG_FLOATMAP) fm = render_image(in, inv->W, inv->H);
+    if (inv->images.at(in).kind != IMG_FLOATMAP) fm = render_image(in, inv->render_w, inv->render_h);
     HostImage src = inv->images.at(fm);
     float sh = (float)fabs((double)(h * src.ax)), sv = (float)fabs((double)(v * src.ay));
     HostImage out = src;
@@ -794,34 +801,82 @@ template <class F> int guarded(F f) {
     return -1;
 }
 
+// Makes the library's stream wait for work the caller's stream still has in flight on this invocation's buffers.
+void wait_for_user_stream(mmb_invocation *inv) {
+    if (!inv->user_event_pending) return;
+    ck(cudaStreamWaitEvent(inv->stream, inv->user_event, 0), "cudaStreamWaitEvent");
+    inv->user_event_pending = false;
+}
+
+// Launches of one entry point go to `user` (the caller's stream) instead of the library's own: the caller's stream
+// first waits for everything init_frame queued, and the library's later work waits for these launches (done()).
+struct StreamScope {
+    mmb_invocation *inv;
+    cudaStream_t saved;
+    bool switched = false;
+    StreamScope(mmb_invocation *i, cudaStream_t user) : inv(i), saved(i->stream) {
+        if (!user || user == saved) return;
+        if (!inv->init_event) ck(cudaEventCreateWithFlags(&inv->init_event, cudaEventDisableTiming), "cudaEventCreate");
+        if (!inv->user_event) ck(cudaEventCreateWithFlags(&inv->user_event, cudaEventDisableTiming), "cudaEventCreate");
+        ck(cudaEventRecord(inv->init_event, saved), "cudaEventRecord");
+        ck(cudaStreamWaitEvent(user, inv->init_event, 0), "cudaStreamWaitEvent");
+        inv->stream = user;
+        switched = true;
+    }
+    void done() {
+        if (!switched) return;
+        ck(cudaEventRecord(inv->user_event, inv->stream), "cudaEventRecord");
+        inv->user_event_pending = true;
+    }
+    ~StreamScope() { inv->stream = saved; }
+};
+
+// calc_lines_<f> for one slice (new_template.c.in:208-312): rows [max(0, first_row), min(last_row, region_y + region_height))
+// and columns [region_x, region_x + region_width) of a frame_w x frame_h frame sampled at the slice's offsets; row r of
+// the band starts at dev_out + (r - first_row) * out_stride, column region_x at its first byte.
+struct SliceGeom {
+    int frame_w, frame_h;
+    int region_x, region_y, region_w, region_h;
+    float off_x, off_y;
+};
+void render_slice(mmb_invocation *inv, const SliceGeom &sl, int first_row, int last_row, void *dev_out, long long out_stride, int floatmap) {
+    if (!inv->frame_ready) fail("mmb_init_frame must be called before mmb_calc_lines");
+    if (sl.frame_w <= 0 || sl.frame_h <= 0 || sl.region_w < 0 || sl.region_h < 0 || sl.region_x < 0 || sl.region_y < 0) fail("bad slice geometry");
+    first_row = std::max(0, first_row);
+    last_row = std::min(last_row, sl.region_y + sl.region_h);
+    if (last_row <= first_row || sl.region_w == 0) return;
+    // the coordinate arrays cover every column / row index the launch reads (a slice may reach past the frame:
+    // the supersampling slice is one column wider, mathmap_common.c:892)
+    LaunchGeom g{sl.frame_w, sl.frame_h, sl.region_x, sl.region_w, first_row, last_row - first_row, sl.off_x, sl.off_y,
+                 std::max(sl.frame_w, sl.region_x + sl.region_w) + 1, std::max(sl.frame_h, last_row) + 1};
+    launch_filter(inv, inv->m->main, inv->main_frame, g, dev_out, out_stride, floatmap, inv->frame, inv->t);
+}
+
+// call_invocation (mathmap_common.c:874-936) for the band [first_row, last_row) of the whole frame: one slice, or with
+// supersampling the short slice plus a one-column-wider slice sampled at (-0.5, -0.5), combined
+// (l1[c] + l1[c+1] + 2 l2[c] + l3[c] + l3[c+1]) / 6.  The long slice has the band's region_height, so the row below
+// the band's last one is clamped away and l3 repeats l1 there -- per band, exactly like the reference's threads.
 void render_band(mmb_invocation *inv, int first_row, int last_row, void *dev_out, int floatmap) {
     if (!inv->frame_ready) fail("mmb_init_frame must be called before mmb_calc_lines");
     first_row = std::max(0, first_row);
-    last_row = std::min(last_row, inv->H);
+    last_row = std::min(last_row, inv->render_h);
     if (last_row <= first_row) return;
-    const Filter *f = inv->m->main;
+    const int W = inv->render_w, H = inv->render_h;
     int rows = last_row - first_row;
     if (inv->cfg.supersampling && !floatmap) {
-        // call_invocation, mathmap_common.c:880-927: the short slice plus a one-column-wider
-        // slice sampled at (-0.5, -0.5), combined (l1[c] + l1[c+1] + 2 l2[c] + l3[c] + l3[c+1]) / 6
         int bpp = inv->bpp;
-        int long_rows = std::min(last_row + 1, inv->H) - first_row;
-        void *s = inv->ensure_staging(inv->staging2, inv->staging2_bytes, (size_t)rows * inv->W * bpp + (size_t)(rows + 1) * (inv->W + 1) * bpp + 512);
+        void *s = inv->ensure_staging(inv->staging2, inv->staging2_bytes, (size_t)rows * W * bpp + (size_t)rows * (W + 1) * bpp + 512);
         unsigned char *shortimg = (unsigned char *)s;
-        unsigned char *longimg = shortimg + (((size_t)rows * inv->W * bpp + 255) & ~(size_t)255);
-        LaunchGeom gs{inv->W, inv->H, 0, inv->W, first_row, rows, 0.f, 0.f, inv->W + 1, inv->H + 1};
-        launch_filter(inv, f, inv->main_frame, gs, shortimg, (long long)inv->W * bpp, 0, inv->frame, inv->t);
-        LaunchGeom gl{inv->W, inv->H, 0, inv->W + 1, first_row, long_rows, -0.5f, -0.5f, inv->W + 1, inv->H + 1};
-        launch_filter(inv, f, inv->main_frame, gl, longimg, (long long)(inv->W + 1) * bpp, 0, inv->frame, inv->t);
-        // rows of the long image beyond what was rendered repeat the last one
-        launch_supersample_combine(shortimg, longimg, (unsigned char *)dev_out, inv->W, rows, long_rows, bpp, inv->stream);
+        unsigned char *longimg = shortimg + (((size_t)rows * W * bpp + 255) & ~(size_t)255);
+        render_slice(inv, SliceGeom{W, H, 0, first_row, W, rows, 0.f, 0.f}, first_row, last_row, shortimg, (long long)W * bpp, 0);
+        render_slice(inv, SliceGeom{W, H, 0, first_row, W + 1, rows, -0.5f, -0.5f}, first_row, last_row, longimg, (long long)(W + 1) * bpp, 0);
+        launch_supersample_combine(shortimg, longimg, (unsigned char *)dev_out, W, rows, rows, bpp, inv->stream);
         inv->launches++;
         ck(cudaGetLastError(), "supersample combine");
         return;
     }
-    LaunchGeom g{inv->W, inv->H, 0, inv->W, first_row, rows, 0.f, 0.f, inv->W + 1, inv->H + 1};
-    long long stride = floatmap ? (long long)sizeof(float) * 4 * inv->W : (long long)inv->W * inv->bpp;
-    launch_filter(inv, f, inv->main_frame, g, dev_out, stride, floatmap, inv->frame, inv->t);
+    long long stride = floatmap ? (long long)sizeof(float) * 4 * W : (long long)W * inv->bpp;
+    render_slice(inv, SliceGeom{W, H, 0, first_row, W, rows, 0.f, 0.f}, first_row, last_row, dev_out, stride, floatmap);
 }
 
 }  // namespace
@@ -858,8 +913,8 @@ mmb_invocation *mmb_invoke(mmb_module *m, int img_width, int img_height, int dev
     int rc = guarded([&] {
         inv->m = m;
         inv->device = device;
-        inv->W = img_width;
-        inv->H = img_height;
+        inv->W = inv->render_w = img_width;
+        inv->H = inv->render_h = img_height;
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0)
@@ -900,6 +955,7 @@ mmb_invocation *mmb_invoke(mmb_module *m, int img_width, int img_height, int dev
 void mmb_invocation_free(mmb_invocation *inv) {
     if (!inv) return;
     cudaSetDevice(inv->device);
+    if (inv->user_event_pending) cudaEventSynchronize(inv->user_event);
     cudaStreamSynchronize(inv->stream);
     inv->release_frame_blocks();
     for (auto &b : inv->free_blocks) cudaFree(b.second);
@@ -911,6 +967,8 @@ void mmb_invocation_free(mmb_invocation *inv) {
     for (auto e : inv->chunk_events) cudaEventDestroy(e);
     if (inv->aux_stream) cudaStreamDestroy(inv->aux_stream);
     if (inv->order_event) cudaEventDestroy(inv->order_event);
+    if (inv->init_event) cudaEventDestroy(inv->init_event);
+    if (inv->user_event) cudaEventDestroy(inv->user_event);
     if (inv->copy_stream) cudaStreamDestroy(inv->copy_stream);
     if (inv->staging) cudaFree(inv->staging);
     if (inv->staging2) cudaFree(inv->staging2);
@@ -919,20 +977,50 @@ void mmb_invocation_free(mmb_invocation *inv) {
     delete inv;
 }
 
-int mmb_set_antialiasing(mmb_invocation *inv, int enabled) { inv->cfg.aa = enabled ? 1 : 0; return 0; }
-int mmb_set_supersampling(mmb_invocation *inv, int enabled) { inv->cfg.supersampling = enabled ? 1 : 0; return 0; }
-int mmb_set_precise_math(mmb_invocation *inv, int enabled) { inv->cfg.precise = enabled ? 1 : 0; return 0; }
+static bool null_inv(const mmb_invocation *inv, const char *fn) {
+    if (inv) return false;
+    set_error(std::string(fn) + ": NULL invocation");
+    return true;
+}
+int mmb_set_antialiasing(mmb_invocation *inv, int enabled) {
+    if (null_inv(inv, "mmb_set_antialiasing")) return -1;
+    inv->cfg.aa = enabled ? 1 : 0;
+    return 0;
+}
+int mmb_set_supersampling(mmb_invocation *inv, int enabled) {
+    if (null_inv(inv, "mmb_set_supersampling")) return -1;
+    inv->cfg.supersampling = enabled ? 1 : 0;
+    return 0;
+}
+int mmb_set_precise_math(mmb_invocation *inv, int enabled) {
+    if (null_inv(inv, "mmb_set_precise_math")) return -1;
+    inv->cfg.precise = enabled ? 1 : 0;
+    return 0;
+}
+// invocation->render_width / render_height: the size frames are rendered at when it differs from the image size (the
+// GIMP preview, mathmap.c:2191-2223); natives render their intermediates at this size (gauss.c:657, convolve.c:88)
+int mmb_set_render_size(mmb_invocation *inv, int render_width, int render_height) {
+    if (null_inv(inv, "mmb_set_render_size")) return -1;
+    if (render_width <= 0 || render_height <= 0) { set_error("mmb_set_render_size: bad size"); return -1; }
+    inv->render_w = render_width;
+    inv->render_h = render_height;
+    inv->frame_ready = false;
+    return 0;
+}
 int mmb_set_warp_shape(mmb_invocation *inv, int warp_width) {
+    if (null_inv(inv, "mmb_set_warp_shape")) return -1;
     if (warp_width != 32 && warp_width != 16 && warp_width != 8) { set_error("warp width must be 32, 16 or 8"); return -1; }
     inv->cfg.warp_w = warp_width;
     return 0;
 }
 int mmb_set_rows_per_thread(mmb_invocation *inv, int rows) {
+    if (null_inv(inv, "mmb_set_rows_per_thread")) return -1;
     if (rows != 0 && rows != 1 && rows != 2 && rows != 4 && rows != 8) { set_error("rows per thread must be 0 (automatic), 1, 2, 4 or 8"); return -1; }
     inv->cfg.rows = rows;
     return 0;
 }
 int mmb_set_edge_behaviour(mmb_invocation *inv, int mode_x, int mode_y, uint32_t color_x, uint32_t color_y) {
+    if (null_inv(inv, "mmb_set_edge_behaviour")) return -1;
     if (mode_x < 0 || mode_x > 3 || mode_y < 0 || mode_y > 3) { set_error("bad edge behaviour"); return -1; }
     inv->cfg.edge_x = mode_x;
     inv->cfg.edge_y = mode_y;
@@ -941,6 +1029,7 @@ int mmb_set_edge_behaviour(mmb_invocation *inv, int mode_x, int mode_y, uint32_t
     return 0;
 }
 int mmb_set_output_bpp(mmb_invocation *inv, int bpp) {
+    if (null_inv(inv, "mmb_set_output_bpp")) return -1;
     if (bpp < 1 || bpp > 4) { set_error("output bpp must be 1..4"); return -1; }
     inv->bpp = bpp;
     return 0;
@@ -980,6 +1069,12 @@ int mmb_set_userval_color(mmb_invocation *inv, int index, float r, float g, floa
     u->color = (q(r) << 24) | (q(g) << 16) | (q(b) << 8) | q(a);
     return 0;
 }
+int mmb_set_userval_color_packed(mmb_invocation *inv, int index, uint32_t rgba_packed) {
+    Userval *u = userval_slot(inv, index, UV_COLOR);
+    if (!u) return -1;
+    u->color = rgba_packed;
+    return 0;
+}
 static int set_table(mmb_invocation *inv, int index, int type, const void *host, size_t bytes) {
     Userval *u = userval_slot(inv, index, type);
     if (!u) return -1;
@@ -1002,6 +1097,7 @@ static int set_image(mmb_invocation *inv, int index, const void *data, bool host
     if (width <= 0 || height <= 0 || !data) { set_error("bad image"); return -1; }
     return guarded([&] {
         set_device(inv);
+        wait_for_user_stream(inv);  // a caller's stream may still sample the image this call replaces
         if (inv->images.size() != inv->persistent_images) {  // drop per-frame images before touching the persistent prefix
             inv->images.resize(inv->persistent_images);
             inv->native_cache.clear();
@@ -1056,7 +1152,9 @@ int mmb_init_frame(mmb_invocation *inv, int frame, float t) {
                 // the reference samples white from a missing drawable (builtins.c:125-126); we require the binding
                 fail("image argument `" + inv->m->main->uservals[i].name + "' has no drawable bound");
             }
-        // previous frame's temporaries become reusable (same stream: ordering is preserved)
+        // previous frame's temporaries become reusable: in stream order on the library's stream, and after whatever a
+        // caller's stream still runs on them
+        wait_for_user_stream(inv);
         inv->release_frame_blocks();
         inv->images.resize(inv->persistent_images);
         inv->native_cache.clear();
@@ -1074,15 +1172,9 @@ int mmb_calc_lines_device(mmb_invocation *inv, int first_row, int last_row, void
     if (!inv || !device_q) { set_error("mmb_calc_lines_device: bad arguments"); return -1; }
     return guarded([&] {
         set_device(inv);
-        cudaStream_t saved = inv->stream;
-        if (stream) inv->stream = (cudaStream_t)stream;
-        try {
-            render_band(inv, first_row, last_row, device_q, floatmap);
-        } catch (...) {
-            inv->stream = saved;
-            throw;
-        }
-        inv->stream = saved;
+        StreamScope scope(inv, (cudaStream_t)stream);
+        render_band(inv, first_row, last_row, device_q, floatmap);
+        scope.done();
     });
 }
 
@@ -1095,118 +1187,162 @@ int mmb_calc_lines_interleaved_device(mmb_invocation *inv, int phase, int count,
         set_device(inv);
         if (!inv->frame_ready) fail("mmb_init_frame must be called before rendering");
         if (inv->cfg.supersampling) fail("interleaved bands do not support supersampling");
-        int blocks = (inv->H + 7) / 8;
+        int blocks = (inv->render_h + 7) / 8;
         int mine = blocks > phase ? (blocks - phase + count - 1) / count : 0;
         if (mine == 0) return;
-        cudaStream_t saved = inv->stream;
-        if (stream) inv->stream = (cudaStream_t)stream;
-        LaunchGeom g{inv->W, inv->H, 0, inv->W, 0, mine * 8, 0.f, 0.f, inv->W + 1, inv->H + 1};
+        StreamScope scope(inv, (cudaStream_t)stream);
+        LaunchGeom g{inv->render_w, inv->render_h, 0, inv->render_w, 0, mine * 8, 0.f, 0.f, inv->render_w + 1, inv->render_h + 1};
         g.interleave = count;
         g.phase = phase;
-        g.row_limit = inv->H;
-        try {
-            launch_filter(inv, inv->m->main, inv->main_frame, g, device_q, (long long)inv->W * inv->bpp, 0, inv->frame, inv->t);
-        } catch (...) {
-            inv->stream = saved;
-            throw;
-        }
-        inv->stream = saved;
+        g.row_limit = inv->render_h;
+        launch_filter(inv, inv->m->main, inv->main_frame, g, device_q, (long long)inv->render_w * inv->bpp, 0, inv->frame, inv->t);
+        scope.done();
     });
+}
+
+// The host-buffer flavour of calc_lines: the band is rendered on the device in chunks and copied into q (row pitch
+// q_pitch bytes).  `sl` = the reference's slice (mmb_calc_lines_slice), or NULL for the whole-frame band of
+// mmb_calc_lines, which also does the supersampling combine of call_invocation.
+static void calc_lines_host(mmb_invocation *inv, const SliceGeom *sl, int first_row, int last_row, void *q, size_t q_pitch, int floatmap) {
+    set_device(inv);
+    const int width = sl ? sl->region_w : inv->render_w;
+    const int row_end = sl ? sl->region_y + sl->region_h : inv->render_h;
+    int fr = std::max(0, first_row), lr = std::min(last_row, row_end);
+    if (lr <= fr || width <= 0) return;
+    size_t row_bytes = floatmap ? sizeof(float) * 4 * (size_t)width : (size_t)width * inv->bpp;
+    size_t bytes = row_bytes * (size_t)(lr - fr);
+    void *d = inv->ensure_staging(inv->staging, inv->staging_bytes, bytes);
+    // The band is rendered in chunks; the device->host copy of a chunk runs on a copy stream while the
+    // kernels of the following chunks run (q pinned: true overlap; pageable q: still correct).  Chunks
+    // alternate between two compute streams, so the last blocks of one chunk (rows of a filter differ in
+    // cost) do not leave the device idle before the next chunk starts.
+    //
+    // Order: kernel then copy is a two-machine flow shop with equal copy times, so the makespan is smallest
+    // when the cheapest chunks are rendered first (Johnson's rule): the copy engine starts early and the
+    // expensive chunks at the end hide the copy backlog.  Chunk costs are measured (time between consecutive
+    // completions) and reused by the next call on the same band, e.g. the next frame of an animation; the
+    // first call renders from the outside in (top, bottom, second from top, ...).
+    int rows = lr - fr;
+    int chunks = 1;
+    if (!(inv->cfg.supersampling && !sl) && bytes >= ((size_t)8 << 20)) chunks = (int)std::min<size_t>(32, std::max<size_t>(2, bytes >> 25));
+    int chunk_rows = ((rows + chunks - 1) / chunks + 7) & ~7;
+    chunks = (rows + chunk_rows - 1) / chunk_rows;
+    if (!inv->copy_stream) ck(cudaStreamCreateWithFlags(&inv->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!inv->aux_stream) ck(cudaStreamCreateWithFlags(&inv->aux_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!inv->order_event) ck(cudaEventCreate(&inv->order_event), "cudaEventCreate");
+    while ((int)inv->chunk_events.size() < chunks) {
+        cudaEvent_t e;
+        ck(cudaEventCreate(&e), "cudaEventCreate");
+        inv->chunk_events.push_back(e);
+    }
+    std::vector<int> order(chunks);
+    const bool have_costs = inv->cost_fr == fr && inv->cost_lr == lr && inv->cost_chunk_rows == chunk_rows && inv->cost_floatmap == floatmap &&
+                            inv->cost_width == width && (int)inv->chunk_cost.size() == chunks;
+    if (have_costs) {
+        for (int i = 0; i < chunks; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return inv->chunk_cost[a] < inv->chunk_cost[b]; });
+    } else {
+        for (int i = 0, lo = 0, hi = chunks - 1; i < chunks; ++i) order[i] = (i & 1) ? hi-- : lo++;
+    }
+    cudaStream_t main_stream = inv->stream;
+    ck(cudaEventRecord(inv->order_event, main_stream), "cudaEventRecord");
+    // everything queued so far (init_frame's renders and blurs) precedes the chunks on both streams
+    if (chunks > 1) ck(cudaStreamWaitEvent(inv->aux_stream, inv->order_event, 0), "cudaStreamWaitEvent");
+    try {
+        for (int k = 0; k < chunks; ++k) {
+            const int ci = order[k];
+            const int r0 = fr + ci * chunk_rows, r1 = std::min(lr, r0 + chunk_rows);
+            char *dchunk = (char *)d + (size_t)(r0 - fr) * row_bytes;
+            inv->stream = (k & 1) ? inv->aux_stream : main_stream;
+            if (sl) render_slice(inv, *sl, r0, r1, dchunk, (long long)row_bytes, floatmap);
+            else render_band(inv, r0, r1, dchunk, floatmap);
+            ck(cudaEventRecord(inv->chunk_events[ci], inv->stream), "cudaEventRecord");
+            ck(cudaStreamWaitEvent(inv->copy_stream, inv->chunk_events[ci], 0), "cudaStreamWaitEvent");
+            char *qchunk = (char *)q + (size_t)(r0 - fr) * q_pitch;
+            if (q_pitch == row_bytes)
+                ck(cudaMemcpyAsync(qchunk, dchunk, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, inv->copy_stream), "cudaMemcpyAsync(D2H)");
+            else
+                ck(cudaMemcpy2DAsync(qchunk, q_pitch, dchunk, row_bytes, row_bytes, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, inv->copy_stream),
+                   "cudaMemcpy2DAsync(D2H)");
+        }
+    } catch (...) {
+        inv->stream = main_stream;
+        throw;
+    }
+    inv->stream = main_stream;
+    ck(cudaStreamSynchronize(inv->aux_stream), "cudaStreamSynchronize");
+    ck(cudaStreamSynchronize(inv->copy_stream), "cudaStreamSynchronize");
+    ck(cudaStreamSynchronize(inv->stream), "cudaStreamSynchronize");
+    if (chunks > 1) {
+        inv->chunk_cost.assign(chunks, 0.0f);
+        cudaEvent_t prev = inv->order_event;
+        for (int k = 0; k < chunks; ++k) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, prev, inv->chunk_events[order[k]]) != cudaSuccess) ms = 0.0f;
+            inv->chunk_cost[order[k]] = ms > 0.0f ? ms : 0.0f;  // a chunk that finished before its predecessor: no cost of its own
+            if (ms > 0.0f) prev = inv->chunk_events[order[k]];
+        }
+        inv->cost_fr = fr; inv->cost_lr = lr; inv->cost_chunk_rows = chunk_rows; inv->cost_floatmap = floatmap; inv->cost_width = width;
+    }
 }
 
 int mmb_calc_lines(mmb_invocation *inv, int first_row, int last_row, void *q, int floatmap) {
     if (!inv || !q) { set_error("mmb_calc_lines: bad arguments"); return -1; }
     return guarded([&] {
+        size_t row_bytes = floatmap ? sizeof(float) * 4 * (size_t)inv->render_w : (size_t)inv->render_w * inv->bpp;
+        calc_lines_host(inv, nullptr, first_row, last_row, q, row_bytes, floatmap);
+    });
+}
+
+// mathfuncs_t.calc_lines (new_template.c.in:208-312) with the reference's own parameters
+static bool slice_geom(const mmb_slice *s, SliceGeom &g) {
+    if (!s) return false;
+    g = SliceGeom{s->frame_render_width, s->frame_render_height, s->region_x, s->region_y, s->region_width, s->region_height,
+                  s->sampling_offset_x, s->sampling_offset_y};
+    return true;
+}
+int mmb_calc_lines_slice(mmb_invocation *inv, const mmb_slice *slice, int first_row, int last_row, void *q, int floatmap) {
+    SliceGeom g;
+    if (!inv || !q || !slice_geom(slice, g)) { set_error("mmb_calc_lines_slice: bad arguments"); return -1; }
+    return guarded([&] {
+        // q advances by invocation->row_stride per row, or by frame_render_width float[4] pixels for floatmap output
+        // (new_template.c.in:299-302)
+        size_t pitch = floatmap ? sizeof(float) * 4 * (size_t)g.frame_w : (size_t)slice->row_stride;
+        size_t row_bytes = floatmap ? sizeof(float) * 4 * (size_t)g.region_w : (size_t)g.region_w * inv->bpp;
+        if (pitch < row_bytes) fail("mmb_calc_lines_slice: row stride smaller than a row of the region");
+        calc_lines_host(inv, &g, first_row, last_row, q, pitch, floatmap);
+    });
+}
+int mmb_calc_lines_slice_device(mmb_invocation *inv, const mmb_slice *slice, int first_row, int last_row, void *device_q, int floatmap, void *stream) {
+    SliceGeom g;
+    if (!inv || !device_q || !slice_geom(slice, g)) { set_error("mmb_calc_lines_slice_device: bad arguments"); return -1; }
+    return guarded([&] {
         set_device(inv);
-        int fr = std::max(0, first_row), lr = std::min(last_row, inv->H);
-        if (lr <= fr) return;
-        size_t row_bytes = floatmap ? sizeof(float) * 4 * (size_t)inv->W : (size_t)inv->W * inv->bpp;
-        size_t bytes = row_bytes * (size_t)(lr - fr);
-        void *d = inv->ensure_staging(inv->staging, inv->staging_bytes, bytes);
-        // The band is rendered in chunks; the device->host copy of a chunk runs on a copy stream while the
-        // kernels of the following chunks run (q pinned: true overlap; pageable q: still correct).  Chunks
-        // alternate between two compute streams, so the last blocks of one chunk (rows of a filter differ in
-        // cost) do not leave the device idle before the next chunk starts.
-        //
-        // Order: kernel then copy is a two-machine flow shop with equal copy times, so the makespan is smallest
-        // when the cheapest chunks are rendered first (Johnson's rule): the copy engine starts early and the
-        // expensive chunks at the end hide the copy backlog.  Chunk costs are measured (time between consecutive
-        // completions) and reused by the next call on the same band, e.g. the next frame of an animation; the
-        // first call renders from the outside in (top, bottom, second from top, ...).
-        int rows = lr - fr;
-        int chunks = 1;
-        if (!inv->cfg.supersampling && bytes >= ((size_t)8 << 20)) chunks = (int)std::min<size_t>(32, std::max<size_t>(2, bytes >> 25));
-        int chunk_rows = ((rows + chunks - 1) / chunks + 7) & ~7;
-        chunks = (rows + chunk_rows - 1) / chunk_rows;
-        if (!inv->copy_stream) ck(cudaStreamCreateWithFlags(&inv->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        if (!inv->aux_stream) ck(cudaStreamCreateWithFlags(&inv->aux_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        if (!inv->order_event) ck(cudaEventCreate(&inv->order_event), "cudaEventCreate");
-        while ((int)inv->chunk_events.size() < chunks) {
-            cudaEvent_t e;
-            ck(cudaEventCreate(&e), "cudaEventCreate");
-            inv->chunk_events.push_back(e);
-        }
-        std::vector<int> order(chunks);
-        const bool have_costs = inv->cost_fr == fr && inv->cost_lr == lr && inv->cost_chunk_rows == chunk_rows && inv->cost_floatmap == floatmap &&
-                                (int)inv->chunk_cost.size() == chunks;
-        if (have_costs) {
-            for (int i = 0; i < chunks; ++i) order[i] = i;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return inv->chunk_cost[a] < inv->chunk_cost[b]; });
-        } else {
-            for (int i = 0, lo = 0, hi = chunks - 1; i < chunks; ++i) order[i] = (i & 1) ? hi-- : lo++;
-        }
-        cudaStream_t main_stream = inv->stream;
-        ck(cudaEventRecord(inv->order_event, main_stream), "cudaEventRecord");
-        // everything queued so far (init_frame's renders and blurs) precedes the chunks on both streams
-        if (chunks > 1) ck(cudaStreamWaitEvent(inv->aux_stream, inv->order_event, 0), "cudaStreamWaitEvent");
-        try {
-            for (int k = 0; k < chunks; ++k) {
-                const int ci = order[k];
-                const int r0 = fr + ci * chunk_rows, r1 = std::min(lr, r0 + chunk_rows);
-                char *dchunk = (char *)d + (size_t)(r0 - fr) * row_bytes;
-                inv->stream = (k & 1) ? inv->aux_stream : main_stream;
-                render_band(inv, r0, r1, dchunk, floatmap);
-                ck(cudaEventRecord(inv->chunk_events[ci], inv->stream), "cudaEventRecord");
-                ck(cudaStreamWaitEvent(inv->copy_stream, inv->chunk_events[ci], 0), "cudaStreamWaitEvent");
-                ck(cudaMemcpyAsync((char *)q + (size_t)(r0 - fr) * row_bytes, dchunk, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDeviceToHost,
-                                   inv->copy_stream),
-                   "cudaMemcpyAsync(D2H)");
-            }
-        } catch (...) {
-            inv->stream = main_stream;
-            throw;
-        }
-        inv->stream = main_stream;
-        ck(cudaStreamSynchronize(inv->aux_stream), "cudaStreamSynchronize");
-        ck(cudaStreamSynchronize(inv->copy_stream), "cudaStreamSynchronize");
-        ck(cudaStreamSynchronize(inv->stream), "cudaStreamSynchronize");
-        if (chunks > 1) {
-            inv->chunk_cost.assign(chunks, 0.0f);
-            cudaEvent_t prev = inv->order_event;
-            for (int k = 0; k < chunks; ++k) {
-                float ms = 0.0f;
-                if (cudaEventElapsedTime(&ms, prev, inv->chunk_events[order[k]]) != cudaSuccess) ms = 0.0f;
-                inv->chunk_cost[order[k]] = ms > 0.0f ? ms : 0.0f;  // a chunk that finished before its predecessor: no cost of its own
-                if (ms > 0.0f) prev = inv->chunk_events[order[k]];
-            }
-            inv->cost_fr = fr; inv->cost_lr = lr; inv->cost_chunk_rows = chunk_rows; inv->cost_floatmap = floatmap;
-        }
+        long long pitch = floatmap ? (long long)sizeof(float) * 4 * g.frame_w : (long long)slice->row_stride;
+        // RGBA8 pixels are stored as one 32-bit word, float pixels as one 128-bit word
+        if (floatmap ? ((uintptr_t)device_q & 15) != 0 : (inv->bpp == 4 && (((uintptr_t)device_q | (uintptr_t)pitch) & 3) != 0))
+            fail("mmb_calc_lines_slice_device: buffer and row stride must be aligned to the pixel size");
+        StreamScope scope(inv, (cudaStream_t)stream);
+        render_slice(inv, g, first_row, last_row, device_q, pitch, floatmap);
+        scope.done();
     });
 }
 
 int mmb_render_frames_device(mmb_invocation *inv, int n, const int *frames, const float *ts, void *device_q, void *stream) {
-    if (!inv || !device_q || n < 0) { set_error("mmb_render_frames_device: bad arguments"); return -1; }
-    size_t frame_bytes = (size_t)inv->W * inv->H * inv->bpp;
+    if (!inv || !device_q || n < 0 || (n > 0 && !ts)) { set_error("mmb_render_frames_device: bad arguments"); return -1; }
+    size_t frame_bytes = (size_t)inv->render_w * inv->render_h * inv->bpp;
     for (int i = 0; i < n; ++i) {
         if (mmb_init_frame(inv, frames ? frames[i] : i, ts[i]) != 0) return -1;
-        if (mmb_calc_lines_device(inv, 0, inv->H, (char *)device_q + frame_bytes * i, 0, stream) != 0) return -1;
+        if (mmb_calc_lines_device(inv, 0, inv->render_h, (char *)device_q + frame_bytes * i, 0, stream) != 0) return -1;
     }
     return 0;
 }
 
 int mmb_synchronize(mmb_invocation *inv) {
+    if (null_inv(inv, "mmb_synchronize")) return -1;
     return guarded([&] {
         set_device(inv);
+        if (inv->user_event_pending) ck(cudaEventSynchronize(inv->user_event), "cudaEventSynchronize");
         ck(cudaStreamSynchronize(inv->stream), "cudaStreamSynchronize");
         ck(cudaGetLastError(), "kernel execution");
     });

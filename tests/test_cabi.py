@@ -128,3 +128,25 @@ def test_persistent_cubin_cache(tmp_path):
         assert os.path.getsize(path) == plain + 24
     finally:
         mb.set_cubin_cache_dir(None)
+
+
+def test_reference_side_backend_type_checks_against_the_reference_headers():
+    """integration/backends/cuda.c (the file a maintainer adds to the reference: gen_and_load_cuda_code, the IR printer, the
+    three mathfuncs_t functions) is compiled -fsyntax-only against the reference's own compiler-internals.h, mathmap.h,
+    drawable.h and userval.h and against include/mathmap_b200.h.  Needs the reference tree: skipped where it is absent."""
+    import subprocess
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("the reference tree is not on this machine")
+    r = subprocess.run(["sh", os.path.join(ROOT, "integration", "check.sh")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+
+
+def test_null_invocation_is_an_error_not_a_crash():
+    L = mb.lib()
+    assert L.mmb_set_antialiasing(None, 1) != 0
+    assert L.mmb_set_output_bpp(None, 4) != 0
+    assert L.mmb_set_edge_behaviour(None, 0, 0, 0, 0) != 0
+    assert L.mmb_set_render_size(None, 4, 4) != 0
+    assert L.mmb_synchronize(None) != 0
+    assert L.mmb_calc_lines_slice(None, None, 0, 1, None, 0) != 0
+    assert b"NULL" in L.mmb_last_error() or b"bad arguments" in L.mmb_last_error()
