@@ -754,8 +754,7 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
     out.data = inv->alloc(bytes);
     if (sh < 0.5f || sv < 0.5f) {
         void *tmp = inv->alloc(bytes);
-        if (!launch_gauss_rle((const float *)src.data, (float *)tmp, (float *)out.data, src.w, src.h, sh, sv, inv->stream))
-            fail("gaussian blur: unsupported kernel length");
+        launch_gauss_rle((const float *)src.data, (float *)tmp, (float *)out.data, src.w, src.h, sh, sv, inv->alloc(gauss_rle_curve_bytes(sh, sv)), inv->stream);
         inv->launches += 2;
     } else {
         void *scratch = inv->alloc(gauss_iir_scratch_bytes(src.w, src.h));
@@ -1358,12 +1357,13 @@ int mmb_gaussian_blur_device(int device, const float *device_in, float *device_o
         cudaStream_t s = (cudaStream_t)stream;
         size_t bytes = sizeof(float) * 4 * (size_t)width * height;
         if (sigma_h_px < 0.5f || sigma_v_px < 0.5f) {
-            void *tmp = nullptr;
+            void *tmp = nullptr, *curves = nullptr;
             ck(cudaMalloc(&tmp, bytes), "cudaMalloc");
-            bool ok = launch_gauss_rle(device_in, (float *)tmp, device_out, width, height, sigma_h_px, sigma_v_px, s);
+            ck(cudaMalloc(&curves, gauss_rle_curve_bytes(sigma_h_px, sigma_v_px)), "cudaMalloc");
+            launch_gauss_rle(device_in, (float *)tmp, device_out, width, height, sigma_h_px, sigma_v_px, curves, s);
             cudaStreamSynchronize(s);
             cudaFree(tmp);
-            if (!ok) fail("gaussian blur: unsupported kernel length");
+            cudaFree(curves);
         } else {
             void *scratch = nullptr;
             ck(cudaMalloc(&scratch, gauss_iir_scratch_bytes(width, height)), "cudaMalloc(scratch)");

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <vector>
 
 #define MM_AA 0
 #define MM_SUPERSAMPLING 0
@@ -378,8 +379,8 @@ void launch_gauss_iir(const void *in, bool in_is_rgba8, float *out, double *scra
 struct RleCurve {
     int length;
     float total;
-    float curve[8];  // sigma < 0.5 px gives length <= 2; guarded on the host
-    float sum[17];   // sum[-length..length] stored at [i + length]
+    const float *curve;  // device: curve[0..length]
+    const float *sum;    // device: sum[-length..length] stored at [i + length]
 };
 
 __global__ void __launch_bounds__(128) gauss_rle_lines_kernel(const float *in, float *outp, int nlines, int n, long long line_stride, long long elem_stride,
@@ -429,48 +430,60 @@ __global__ void __launch_bounds__(128) gauss_rle_lines_kernel(const float *in, f
     }
 }
 
-static bool make_rle_curve_host(double sigma, RleCurve &K) {
+// make_rle_curve, gauss.c:265-300: the curve reaches out to where it drops below 1/255, whatever that length is
+static int rle_curve_length(double sigma) {
     const double sigma2 = 2 * sigma * sigma;
     const double l = sqrt(-sigma2 * log(1.0 / 255.0));
     int n = (int)(ceil(l) * 2);
     if ((n % 2) == 0) n += 1;
-    int length = n / 2;
-    if (length > 7) return false;
+    return n / 2;
+}
+// floats of device memory one curve takes: curve[0..length] and sum[0..2 length]
+static size_t rle_curve_floats(double sigma) { return 3 * (size_t)rle_curve_length(sigma) + 2; }
+size_t gauss_rle_curve_bytes(float sigma_h, float sigma_v) {
+    return sizeof(float) * ((sigma_h > 0.0f ? rle_curve_floats(sigma_h) : 0) + (sigma_v > 0.0f ? rle_curve_floats(sigma_v) : 0)) + 16;
+}
+static void make_rle_curve(double sigma, RleCurve &K, float *dev, cudaStream_t stream) {
+    const double sigma2 = 2 * sigma * sigma;
+    const int length = rle_curve_length(sigma);
     K.length = length;
-    float curve[17];
+    std::vector<float> curve(2 * (size_t)length + 1), host(rle_curve_floats(sigma));
     curve[length] = 1.0f;
     for (int i = 1; i <= length; i++) {
         float temp = (float)exp(-(i * i) / sigma2);
         curve[length - i] = temp;
         curve[length + i] = temp;
     }
-    for (int i = 0; i <= length; ++i) K.curve[i] = curve[length + i];
-    float sum[18];
-    sum[0] = 0;
-    for (int i = 1; i <= length * 2; i++) sum[i] = curve[i - 1] + sum[i - 1];
-    for (int i = 0; i <= 2 * length; ++i) K.sum[i] = sum[i];
-    K.total = sum[2 * length] - sum[0];
-    return true;
+    float *hc = host.data(), *hs = host.data() + length + 1;
+    for (int i = 0; i <= length; ++i) hc[i] = curve[length + i];
+    hs[0] = 0;
+    for (int i = 1; i <= length * 2; i++) hs[i] = curve[i - 1] + hs[i - 1];
+    K.total = hs[2 * length] - hs[0];
+    K.curve = dev;
+    K.sum = dev + length + 1;
+    // pageable source: the call returns once the bytes are staged, so `host` may go out of scope
+    cudaMemcpyAsync(dev, host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice, stream);
 }
 
-// in and out must be distinct float4 [height][width] buffers; tmp is a third one
-bool launch_gauss_rle(const float *in, float *tmp, float *out, int width, int height, float sigma_h, float sigma_v, cudaStream_t stream) {
+// in and out must be distinct float4 [height][width] buffers; tmp is a third one; curve_mem: gauss_rle_curve_bytes()
+void launch_gauss_rle(const float *in, float *tmp, float *out, int width, int height, float sigma_h, float sigma_v, void *curve_mem, cudaStream_t stream) {
     RleCurve K;
     const float *src = in;
+    float *dev = (float *)curve_mem;
     size_t bytes = sizeof(float) * 4 * (size_t)width * height;
     if (sigma_v > 0.0f) {
-        if (!make_rle_curve_host(sigma_v, K)) return false;
+        make_rle_curve(sigma_v, K, dev, stream);
+        dev += rle_curve_floats(sigma_v);
         int threads = width * 4;
         gauss_rle_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(src, tmp, width, height, 4, (long long)width * 4, K);
         src = tmp;
     }
     if (sigma_h > 0.0f) {
-        if (!make_rle_curve_host(sigma_h, K)) return false;
+        make_rle_curve(sigma_h, K, dev, stream);
         int threads = height * 4;
         gauss_rle_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(src, out, height, width, (long long)width * 4, 4, K);
     } else
         cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToDevice, stream);
-    return true;
 }
 
 // -------------------------------------------------------- supersampling combine

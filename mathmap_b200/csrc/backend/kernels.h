@@ -17,7 +17,8 @@ void launch_drawable_to_bytes(const mm_image &img, void *out, int width, int hei
 bool drawable_render_is_identity(const mm_image &img, int width, int height, float ax, float bx, float ay, float by, int supersampling);
 void launch_gauss_iir(const void *in, bool in_is_rgba8, float *out, double *scratch, int width, int height, float sigma_h, float sigma_v,
                       cudaStream_t stream);
-bool launch_gauss_rle(const float *in, float *tmp, float *out, int width, int height, float sigma_h, float sigma_v, cudaStream_t stream);
+size_t gauss_rle_curve_bytes(float sigma_h, float sigma_v);
+void launch_gauss_rle(const float *in, float *tmp, float *out, int width, int height, float sigma_h, float sigma_v, void *curve_mem, cudaStream_t stream);
 void gauss_iir_constants_host(float std_dev, double *out30);
 void launch_supersample_combine(const unsigned char *shortimg, const unsigned char *longimg, unsigned char *out, int width, int height, int long_rows,
                                 int bpp, cudaStream_t stream);

@@ -252,7 +252,9 @@ def test_fft_native_filters_match_oracle(size):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("w,h,sh,sv", [(383, 257, 6.5, 3.25), (64, 48, 0.75, 12.0), (5, 3, 1.0, 1.0), (1, 1, 2.0, 2.0), (2, 7, 0.5, 0.5),
-                                       (9, 1, 3.0, 3.0), (130, 17, 0.3, 0.4), (31, 33, 0.45, 2.0)])
+                                       (9, 1, 3.0, 3.0), (130, 17, 0.3, 0.4), (31, 33, 0.45, 2.0),
+                                       # one sigma below 0.5 px sends BOTH axes to the FIR (gauss.c:662), whatever the other's length
+                                       (130, 40, 6.0, 0.0), (40, 130, 0.0, 6.0), (64, 64, 0.3, 8.0), (200, 31, 12.0, 0.4)])
 def test_gaussian_blur_device_bit_exact_floats(w, h, sh, sv):
     """mmb_gaussian_blur_device on float data against the oracle's gauss.c restatement, compared as raw float bits.
     Odd, tiny and one-sample lines exercise the meet-in-the-middle hand-over of the two concurrent IIR sweeps."""
