@@ -20,13 +20,14 @@ struct PlanKey {
     int device, h, w, type;
     bool operator<(const PlanKey &o) const { return std::tie(device, h, w, type) < std::tie(o.device, o.h, o.w, o.type); }
 };
+// Plans are shared by the invocations of a process; a plan carries its stream, so one lock covers a native filter
+// from cufftSetStream to the completion of its last transform (fft_convolve etc. hold it for their whole run).
 std::map<PlanKey, cufftHandle> g_plans;
 std::mutex g_plans_mu;
 
 bool get_plan(int h, int w, cufftType type, cudaStream_t stream, cufftHandle *out, std::string &err) {
     int device = 0;
     cudaGetDevice(&device);
-    std::lock_guard<std::mutex> lock(g_plans_mu);
     PlanKey key{device, h, w, (int)type};
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
@@ -50,7 +51,10 @@ __global__ void __launch_bounds__(256) extract_channel_kernel(const float4 *img,
     plane[i] = (double)p[channel];
 }
 
-__global__ void __launch_bounds__(256) sum_kernel(const double *plane, long long n, double *result) {
+// Sum of a plane in a fixed order (the reference adds sequentially, convolve.c:117-122; any fixed order is as
+// good, a run-to-run varying one is not): SUM_BLOCKS partial sums, then one block adds those.
+#define SUM_BLOCKS 1024
+__global__ void __launch_bounds__(256) sum_kernel(const double *plane, long long n, double *partials) {
     __shared__ double sh[256];
     double s = 0.0;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) s += plane[i];
@@ -60,7 +64,19 @@ __global__ void __launch_bounds__(256) sum_kernel(const double *plane, long long
         if (threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
         __syncthreads();
     }
-    if (threadIdx.x == 0) atomicAdd(result, sh[0]);
+    if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double *partials, double *result) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < SUM_BLOCKS; i += 256) s += partials[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *result = sh[0];
 }
 
 __global__ void __launch_bounds__(256) scale_by_inverse_kernel(double *plane, long long n, const double *sum) {
@@ -148,7 +164,7 @@ struct Work {
         if (spec_b) cudaFree(spec_b);
     }
     bool alloc(long long n, long long cn, bool two, std::string &err) {
-        if (cudaMalloc(&plane, sizeof(double) * n) != cudaSuccess || cudaMalloc(&sum, sizeof(double)) != cudaSuccess ||
+        if (cudaMalloc(&plane, sizeof(double) * n) != cudaSuccess || cudaMalloc(&sum, sizeof(double) * (SUM_BLOCKS + 1)) != cudaSuccess ||
             cudaMalloc(&spec_a, sizeof(cufftDoubleComplex) * cn) != cudaSuccess ||
             (two && cudaMalloc(&spec_b, sizeof(cufftDoubleComplex) * cn) != cudaSuccess)) {
             err = "cudaMalloc failed in FFT native filter";
@@ -168,6 +184,7 @@ void launch_floatmap_resample(const float *src, int sw, int sh, float sax, float
 
 bool fft_convolve(const float *in, const float *filt, float *out, int w, int h, int normalize, int copy_alpha, cudaStream_t stream, long *launches,
                   std::string &err) {
+    std::lock_guard<std::mutex> lock(g_plans_mu);
     long long n = (long long)w * h, cn = (long long)h * (w / 2 + 1), nhalf = (long long)w * (h / 2) + w / 2;
     cufftHandle fwd, inv;
     if (!get_plan(h, w, CUFFT_D2Z, stream, &fwd, err) || !get_plan(h, w, CUFFT_Z2D, stream, &inv, err)) return false;
@@ -179,10 +196,10 @@ bool fft_convolve(const float *in, const float *filt, float *out, int w, int h, 
         if (cufftExecD2Z(fwd, wk.plane, wk.spec_a) != CUFFT_SUCCESS) { err = "cufftExecD2Z failed"; return false; }
         extract_channel_kernel<<<blocks(n), 256, 0, stream>>>((const float4 *)filt, wk.plane, n, c, n - nhalf);
         if (normalize) {
-            cudaMemsetAsync(wk.sum, 0, sizeof(double), stream);
-            sum_kernel<<<1024, 256, 0, stream>>>(wk.plane, n, wk.sum);
+            sum_kernel<<<SUM_BLOCKS, 256, 0, stream>>>(wk.plane, n, wk.sum + 1);
+            sum_partials_kernel<<<1, 256, 0, stream>>>(wk.sum + 1, wk.sum);
             scale_by_inverse_kernel<<<blocks(n), 256, 0, stream>>>(wk.plane, n, wk.sum);
-            *launches += 2;
+            *launches += 3;
         }
         if (cufftExecD2Z(fwd, wk.plane, wk.spec_b) != CUFFT_SUCCESS) { err = "cufftExecD2Z failed"; return false; }
         complex_multiply_kernel<<<blocks(cn), 256, 0, stream>>>(wk.spec_a, wk.spec_b, cn);
@@ -196,6 +213,7 @@ bool fft_convolve(const float *in, const float *filt, float *out, int w, int h, 
 }
 
 bool fft_half_convolve(const float *in, const float *mask, float *out, int w, int h, int copy_alpha, cudaStream_t stream, long *launches, std::string &err) {
+    std::lock_guard<std::mutex> lock(g_plans_mu);
     long long n = (long long)w * h, nhalf = (long long)w * (h / 2) + w / 2;
     int cw = w / 2 + 1;
     long long cn = (long long)h * cw;
@@ -219,6 +237,7 @@ bool fft_half_convolve(const float *in, const float *mask, float *out, int w, in
 }
 
 bool fft_visualize(const float *in, float *out, int w, int h, int ignore_alpha, cudaStream_t stream, long *launches, std::string &err) {
+    std::lock_guard<std::mutex> lock(g_plans_mu);
     long long n = (long long)w * h;
     int cw = w / 2 + 1;
     long long cn = (long long)h * cw;

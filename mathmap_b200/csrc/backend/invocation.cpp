@@ -610,7 +610,9 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
 
 int Replay::render_image(int idx, int width, int height, bool force) {
     HostImage src = inv->images.at(idx);
-    if (src.kind == IMG_FLOATMAP && !force) return idx;
+    // a RESIZE wrapper is not a floatmap to the reference (its type is IMAGE_RESIZE, builtins.c:275): it is resampled
+    // through ORIG_VAL with its factors, and the result carries none
+    if (src.kind == IMG_FLOATMAP && !src.resized && !force) return idx;
     HostImage out;
     out.kind = IMG_FLOATMAP;
     out.w = width;
@@ -669,7 +671,10 @@ int Replay::fft_native(const std::string &name, const std::vector<HVal> &args) {
     auto it = inv->native_cache.find(key);
     if (it != inv->native_cache.end()) return it->second;
     int in = args[0].image;
-    if (inv->images.at(in).kind != IMG_FLOATMAP) in = render_image(in, inv->render_w, inv->render_h, true);  // convolve.c:88
+    {
+        const HostImage &i0 = inv->images.at(in);  // convolve.c:88 always re-renders; skipped where that is the identity
+        if (i0.kind != IMG_FLOATMAP || i0.resized || i0.w != inv->render_w || i0.h != inv->render_h) in = render_image(in, inv->render_w, inv->render_h, true);
+    }
     HostImage src = inv->images.at(in);
     HostImage out;
     out.kind = IMG_FLOATMAP;
@@ -686,7 +691,7 @@ int Replay::fft_native(const std::string &name, const std::vector<HVal> &args) {
     } else if (name == "convolve" || name == "half_convolve") {
         int fi = args[1].image;
         const HostImage &f0 = inv->images.at(fi);
-        if (f0.kind != IMG_FLOATMAP || f0.w != src.w || f0.h != src.h) fi = render_image(fi, src.w, src.h, true);
+        if (f0.kind != IMG_FLOATMAP || f0.resized || f0.w != src.w || f0.h != src.h) fi = render_image(fi, src.w, src.h, true);
         HostImage filt = inv->images.at(fi);
         if (name == "convolve")
             ok = fft_convolve((const float *)src.data, (const float *)filt.data, (float *)out.data, src.w, src.h, as_int(args[2]) != 0, as_int(args[3]) != 0,
@@ -745,11 +750,14 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
         }
     }
     int fm = in;
-    if (inv->images.at(in).kind != IMG_FLOATMAP) fm = render_image(in, inv->render_w, inv->render_h);
+    if (inv->images.at(in).kind != IMG_FLOATMAP || inv->images.at(in).resized) fm = render_image(in, inv->render_w, inv->render_h);
     HostImage src = inv->images.at(fm);
     float sh = (float)fabs((double)(h * src.ax)), sv = (float)fabs((double)(v * src.ay));
     HostImage out = src;
     out.owned = false;
+    out.xf = out.yf = 1.f;  // a native filter's result is a plain floatmap (gauss.c:147 floatmap_copy)
+    out.resized = false;
+    out.original = -1;
     size_t bytes = sizeof(float) * 4 * (size_t)src.w * src.h;
     out.data = inv->alloc(bytes);
     if (sh < 0.5f || sv < 0.5f) {

@@ -130,3 +130,30 @@ def test_user_stream_is_ordered_after_init_frame_work():
     stream.synchronize()
     for i in range(3):
         assert np.array_equal(frames[i].cpu().numpy(), want), i
+
+
+RESIZED_FLOATMAP = """
+filter inner (pixel image im, float s: 0-1 (0.02))
+  b = gaussian_blur(im, s, s);
+  b(xy)
+end
+filter outer (image in)
+  rendered = render(in);
+  inner(rendered, 0.02, xy)
+end
+"""
+
+
+def test_native_filter_on_a_resize_wrapped_floatmap():
+    """a RESIZE wrapper around a floatmap (an image argument whose coordinate flags differ from the filter's,
+    compiler.c:1710-1773) is not a floatmap to render_image / gaussian_blur (builtins.c:275, gauss.c:655-657): it is resampled
+    with the factors first and the blurred result carries none."""
+    W, H = 160, 96
+    img = synthetic_rgba(W, H)
+    m = mb.Module(source=RESIZED_FLOATMAP)
+    inv = mb.Invocation(m, W, H, antialiasing=True)
+    inv.set("in", img)
+    got = inv.render(0, 0.0)
+    want = OracleFilter(m.ir).render(W, H, {"in": img}, antialiasing=True)
+    exact, le1, mx = compare_u8(got, want)
+    assert exact >= 99.99, (exact, le1, mx)
