@@ -1266,7 +1266,7 @@ static void calc_lines_host(mmb_invocation *inv, const SliceGeom *sl, int first_
             ck(cudaEventRecord(inv->chunk_events[ci], inv->stream), "cudaEventRecord");
             ck(cudaStreamWaitEvent(inv->copy_stream, inv->chunk_events[ci], 0), "cudaStreamWaitEvent");
             char *qchunk = (char *)q + (size_t)(r0 - fr) * q_pitch;
-            if (q_pitch == row_bytes)
+            if (q_pitch == row_bytes || r1 - r0 == 1)
                 ck(cudaMemcpyAsync(qchunk, dchunk, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, inv->copy_stream), "cudaMemcpyAsync(D2H)");
             else
                 ck(cudaMemcpy2DAsync(qchunk, q_pitch, dchunk, row_bytes, row_bytes, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, inv->copy_stream),
@@ -1316,7 +1316,10 @@ int mmb_calc_lines_slice(mmb_invocation *inv, const mmb_slice *slice, int first_
         // (new_template.c.in:299-302)
         size_t pitch = floatmap ? sizeof(float) * 4 * (size_t)g.frame_w : (size_t)slice->row_stride;
         size_t row_bytes = floatmap ? sizeof(float) * 4 * (size_t)g.region_w : (size_t)g.region_w * inv->bpp;
-        if (pitch < row_bytes) fail("mmb_calc_lines_slice: row stride smaller than a row of the region");
+        // one row may be wider than the stride: the reference's supersampling loop renders its region_width + 1 lines one
+        // at a time into line buffers of their own (mathmap_common.c:897-905) with the frame's row_stride
+        const int rows = std::min(last_row, g.region_y + g.region_h) - std::max(0, first_row);
+        if (pitch < row_bytes && rows > 1) fail("mmb_calc_lines_slice: row stride smaller than a row of the region");
         calc_lines_host(inv, &g, first_row, last_row, q, pitch, floatmap);
     });
 }

@@ -465,7 +465,7 @@ static void make_rle_curve(double sigma, RleCurve &K, float *dev, cudaStream_t s
     cudaMemcpyAsync(dev, host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice, stream);
 }
 
-// in and out must be distinct float4 [height][width] buffers; tmp is a third one; curve_mem: gauss_rle_curve_bytes()
+// in -> out (float4 [height][width], may alias); tmp is a third buffer of that size; curve_mem: gauss_rle_curve_bytes()
 void launch_gauss_rle(const float *in, float *tmp, float *out, int width, int height, float sigma_h, float sigma_v, void *curve_mem, cudaStream_t stream) {
     RleCurve K;
     const float *src = in;
@@ -481,7 +481,11 @@ void launch_gauss_rle(const float *in, float *tmp, float *out, int width, int he
     if (sigma_h > 0.0f) {
         make_rle_curve(sigma_h, K, dev, stream);
         int threads = height * 4;
-        gauss_rle_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(src, out, height, width, (long long)width * 4, 4, K);
+        // a pass never runs in place (every output sample reads its neighbours): when the horizontal pass is the only
+        // one and the caller's buffers alias, it goes through tmp
+        float *dst = src == out ? tmp : out;
+        gauss_rle_lines_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(src, dst, height, width, (long long)width * 4, 4, K);
+        if (dst != out) cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToDevice, stream);
     } else
         cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToDevice, stream);
 }
