@@ -695,6 +695,18 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         if (have_rows) fn << rv_load.str();
         if (e.direct_sample) fn << "    unsigned mm_word = 0; bool mm_have_word = false;\n";
         for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
+        if (e.direct_sample) {
+            // img(xy) with x, y the pixel's own coordinates and a frame-constant image and frame
+            const Rhs *r = e.direct_sample->rhs;
+            auto internal_is = [](const Primary &p, const char *name) {
+                return !p.is_const && p.value->index >= 0 && p.value->def && p.value->def->kind == ST_ASSIGN && p.value->def->rhs->kind == RHS_INTERNAL &&
+                       p.value->def->rhs->internal == name;
+            };
+            const Primary &im = r->args[2], &tt = r->args[3];
+            if (internal_is(r->args[0], "x") && internal_is(r->args[1], "y") && !im.is_const && im.value->index >= 0 && im.value->level == 0 &&
+                (tt.is_const || tt.value->index < 0 || tt.value->level == 0))
+                k.passthrough_image = im.value;
+        }
         fn << body
            << (e.direct_sample ? "    if (mm_have_word) mm_store_word(mm_outp, col, mm_word); else\n" : "")
            << "    mm_store_pixel(P, mm_outp, col, mm_ret);\n"

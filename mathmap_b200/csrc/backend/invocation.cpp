@@ -63,6 +63,11 @@ struct HostImage {
     int original = -1;  // for resize wrappers: the wrapped image
     const Filter *filter = nullptr;
     std::vector<HVal> args;
+    // A Gaussian blur (IIR) whose horizontal pass has not run yet: `data` holds the vertical pass's result.  The pass is
+    // run in place by materialise() when anything reads the image, or -- when the frame's pixels ARE this image's
+    // (pass-through, see render_slice) -- band by band straight into the caller's rows.
+    bool pending_rows = false;
+    float pending_sigma_h = 0.f;
 };
 
 struct Userval {
@@ -103,6 +108,8 @@ struct mmb_invocation {
     float t = 0.f;
     bool frame_ready = false;
     FrameData main_frame;
+    int passthrough_image = -1;  // this frame's pixels are the floatmap images[passthrough_image], sampled at their own positions
+    std::map<std::string, bool> identity_cache;
     long launches = 0;
     std::string kernel_name;
     std::map<std::string, float *> coord_cache;
@@ -202,6 +209,44 @@ mm_image to_device_desc(const HostImage &h) {
     d.fast_hm1 = fast ? (float)(h.h - 1) : -1.0f;
     d.fast_nf = fast ? (float)h.num_frames : -1.0f;
     return d;
+}
+
+// Runs the pending horizontal pass of a deferred Gaussian blur in place (see HostImage::pending_rows).
+void materialise(mmb_invocation *inv, int image) {
+    if (image < 0 || image >= (int)inv->images.size()) return;
+    HostImage &im = inv->images[image];
+    if (!im.pending_rows) return;
+    void *scratch = inv->alloc(gauss_iir_scratch_bytes(im.w, im.h));
+    launch_gauss_iir_rows((const float *)im.data, im.data, false, (long long)im.w * 16, (double *)scratch, im.w, 0, im.h, im.pending_sigma_h, inv->stream);
+    ck(cudaGetLastError(), "gaussian blur (rows) launch");
+    inv->launches++;
+    im.pending_rows = false;
+}
+
+// Does get_floatmap_pixel (builtins.c:249-265) at the virtual coordinates of pixel (x, y) of a w x h frame read texel
+// (x, y) of this floatmap, for every pixel?  Decided with the device's own float operations (mm_floatmap_pixel:
+// rintf(ax * X + bx)) on the host's copy of the coordinate arrays (CALC_VIRTUAL_X/Y, see coords()).
+bool floatmap_lookup_is_identity(mmb_invocation *inv, const HostImage &im, int w, int h) {
+    if (im.kind != IMG_FLOATMAP || im.resized || im.xf != 1.f || im.yf != 1.f || im.w != w || im.h != h || w < 2 || h < 2) return false;
+    char key[160];
+    snprintf(key, sizeof key, "%d_%d_%a_%a_%a_%a", w, h, (double)im.ax, (double)im.bx, (double)im.ay, (double)im.by);
+    auto it = inv->identity_cache.find(key);
+    if (it != inv->identity_cache.end()) return it->second;
+    bool ok = true;
+    for (int x = 0; x < w && ok; ++x) {
+        volatile float X = (float)(((x) - ((w)-1) / 2.0 + 0.0) / (((w)-1) / 2.0));
+        volatile float p = im.ax * X;
+        volatile float f = p + im.bx;
+        ok = f > -2147483904.0f && f < 2147483648.0f && (int)rintf(f) == x;
+    }
+    for (int y = 0; y < h && ok; ++y) {
+        volatile float Y = (float)((-(y) + ((h)-1) / 2.0 - 0.0) / (((h)-1) / 2.0));
+        volatile float p = im.ay * Y;
+        volatile float f = p + im.by;
+        ok = f > -2147483904.0f && f < 2147483648.0f && (int)rintf(f) == y;
+    }
+    inv->identity_cache[key] = ok;
+    return ok;
 }
 
 // -------------------------------------------------------------- host replay
@@ -437,6 +482,7 @@ void pack_uniform_bytes(mmb_invocation *inv, const FilterKernel &k, Replay &rp, 
 // mm_closure_<filter> through mm_closure_dispatch.
 mm_image device_desc(mmb_invocation *inv, FrameData &fd, int image, float t, int depth) {
     if (image < 0 || image >= (int)inv->images.size()) fail("internal error: bad image handle");
+    if (image != inv->passthrough_image) materialise(inv, image);  // the pass-through image keeps its horizontal pass for the band launches
     if (inv->images[image].kind != IMG_CLOSURE) return to_device_desc(inv->images[image]);
     if (depth > 16) fail("closure nesting too deep");
     const HostImage img = inv->images[image];  // copy: the replay below may add images
@@ -609,6 +655,7 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
 }
 
 int Replay::render_image(int idx, int width, int height, bool force) {
+    materialise(inv, idx);
     HostImage src = inv->images.at(idx);
     // a RESIZE wrapper is not a floatmap to the reference (its type is IMAGE_RESIZE, builtins.c:275): it is resampled
     // through ORIG_VAL with its factors, and the result carries none
@@ -671,6 +718,8 @@ int Replay::fft_native(const std::string &name, const std::vector<HVal> &args) {
     auto it = inv->native_cache.find(key);
     if (it != inv->native_cache.end()) return it->second;
     int in = args[0].image;
+    materialise(inv, in);
+    if (args.size() > 1 && args[1].image >= 0) materialise(inv, args[1].image);
     {
         const HostImage &i0 = inv->images.at(in);  // convolve.c:88 always re-renders; skipped where that is the identity
         if (i0.kind != IMG_FLOATMAP || i0.resized || i0.w != inv->render_w || i0.h != inv->render_h) in = render_image(in, inv->render_w, inv->render_h, true);
@@ -715,6 +764,7 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
     snprintf(key, sizeof key, "gauss:%d:%a:%a", in, (double)h, (double)v);
     auto it = inv->native_cache.find(key);
     if (it != inv->native_cache.end()) return it->second;
+    materialise(inv, in);
     // A drawable input whose blur takes the IIR path is not rendered to a floatmap first: every channel of that
     // floatmap would be k/255 of a byte, so the column pass reads RGBA8 (the drawable itself when render_image is the
     // identity on texels, else a resampled RGBA8 copy) and converts on load; results are the same floats.
@@ -740,9 +790,13 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
                 inv->launches++;
                 bytes_in = resampled;
             }
+            // the vertical pass now, the horizontal one when the image is first read (materialise) or, band by band, as
+            // the frame's own pixels (render_slice)
             void *scratch = inv->alloc(gauss_iir_scratch_bytes(w, hgt));
-            launch_gauss_iir(bytes_in, true, (float *)out.data, (double *)scratch, w, hgt, sh, sv, inv->stream);
-            inv->launches += 2;
+            launch_gauss_iir_columns(bytes_in, true, (float *)out.data, (double *)scratch, w, hgt, sv, inv->stream);
+            inv->launches++;
+            out.pending_rows = true;
+            out.pending_sigma_h = sh;
             ck(cudaGetLastError(), "gaussian blur launch");
             int idx = add_image(out);
             inv->native_cache[key] = idx;
@@ -758,6 +812,7 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
     out.xf = out.yf = 1.f;  // a native filter's result is a plain floatmap (gauss.c:147 floatmap_copy)
     out.resized = false;
     out.original = -1;
+    out.pending_rows = false;
     size_t bytes = sizeof(float) * 4 * (size_t)src.w * src.h;
     out.data = inv->alloc(bytes);
     if (sh < 0.5f || sv < 0.5f) {
@@ -766,8 +821,10 @@ int Replay::gaussian_blur(const std::vector<HVal> &args) {
         inv->launches += 2;
     } else {
         void *scratch = inv->alloc(gauss_iir_scratch_bytes(src.w, src.h));
-        launch_gauss_iir(src.data, false, (float *)out.data, (double *)scratch, src.w, src.h, sh, sv, inv->stream);
-        inv->launches += 2;
+        launch_gauss_iir_columns(src.data, false, (float *)out.data, (double *)scratch, src.w, src.h, sv, inv->stream);
+        inv->launches++;
+        out.pending_rows = true;
+        out.pending_sigma_h = sh;
     }
     ck(cudaGetLastError(), "gaussian blur launch");
     int idx = add_image(out);
@@ -852,6 +909,24 @@ void render_slice(mmb_invocation *inv, const SliceGeom &sl, int first_row, int l
     first_row = std::max(0, first_row);
     last_row = std::min(last_row, sl.region_y + sl.region_h);
     if (last_row <= first_row || sl.region_w == 0) return;
+    if (inv->passthrough_image >= 0) {
+        HostImage &im = inv->images[inv->passthrough_image];
+        if (im.pending_rows && sl.region_x == 0 && sl.region_w == im.w && sl.frame_w == im.w && sl.frame_h == im.h && sl.off_x == 0.f && sl.off_y == 0.f &&
+            last_row <= im.h && (floatmap || inv->bpp == 4)) {
+            // whole rows of the frame at the frame's own sampling positions: the blur's horizontal pass over these rows
+            // writes them (quantised like mm_store_pixel, or as floats); chunks may run on different streams, so each
+            // launch has checkpoint memory of its own
+            const int rows = last_row - first_row;
+            void *scratch = inv->alloc(gauss_iir_scratch_bytes(im.w, rows));
+            launch_gauss_iir_rows((const float *)im.data, dev_out, !floatmap, out_stride, (double *)scratch, im.w, first_row, rows, im.pending_sigma_h,
+                                  inv->stream);
+            ck(cudaGetLastError(), "gaussian blur (rows) launch");
+            inv->launches++;
+            inv->kernel_name = "gauss_iir_rows";
+            return;
+        }
+        materialise(inv, inv->passthrough_image);  // anything else samples the finished floatmap through the pixel kernel
+    }
     // the coordinate arrays cover every column / row index the launch reads (a slice may reach past the frame:
     // the supersampling slice is one column wider, mathmap_common.c:892)
     LaunchGeom g{sl.frame_w, sl.frame_h, sl.region_x, sl.region_w, first_row, last_row - first_row, sl.off_x, sl.off_y,
@@ -1168,9 +1243,21 @@ int mmb_init_frame(mmb_invocation *inv, int frame, float t) {
         inv->frame = frame;
         inv->t = t;
         std::vector<HVal> uv = main_uservals(inv);
+        inv->passthrough_image = -1;
         Replay rp(inv, inv->m->main, uv, frame, t, 0);
         rp.run(rp.code->first);
-        pack_frame(inv, inv->backend->source.kernels.at(inv->m->main), rp, inv->main_frame);
+        const FilterKernel &mk = inv->backend->source.kernels.at(inv->m->main);
+        // Pass-through: the filter's pixel is `img(xy)` (cuda_emit.cpp) and img is a blur whose horizontal pass is still
+        // pending and whose texel (x, y) is what pixel (x, y) looks up.  That pass then writes the frame's rows itself
+        // (render_slice) instead of a floatmap the pixel kernel would only copy and quantise.
+        if (mk.passthrough_image) {
+            auto it = rp.env.find(mk.passthrough_image);
+            if (it != rp.env.end() && it->second.image >= 0 && it->second.image < (int)inv->images.size()) {
+                const HostImage &im = inv->images[it->second.image];
+                if (im.pending_rows && floatmap_lookup_is_identity(inv, im, inv->render_w, inv->render_h)) inv->passthrough_image = it->second.image;
+            }
+        }
+        pack_frame(inv, mk, rp, inv->main_frame);
         inv->frame_ready = true;
     });
 }
@@ -1197,6 +1284,7 @@ int mmb_calc_lines_interleaved_device(mmb_invocation *inv, int phase, int count,
         int blocks = (inv->render_h + 7) / 8;
         int mine = blocks > phase ? (blocks - phase + count - 1) / count : 0;
         if (mine == 0) return;
+        materialise(inv, inv->passthrough_image);
         StreamScope scope(inv, (cudaStream_t)stream);
         LaunchGeom g{inv->render_w, inv->render_h, 0, inv->render_w, 0, mine * 8, 0.f, 0.f, inv->render_w + 1, inv->render_h + 1};
         g.interleave = count;

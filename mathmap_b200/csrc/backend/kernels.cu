@@ -343,11 +343,11 @@ void gauss_iir_constants_host(float std_dev, double *out30) {
     memcpy(out30, &c, sizeof(double) * 30);
 }
 
-size_t gauss_iir_scratch_bytes(int width, int height) { return sizeof(double) * 4 * (size_t)width * height; }
+size_t gauss_iir_scratch_bytes_r01(int width, int height) { return sizeof(double) * 4 * (size_t)width * height; }
 
 // in -> out (float4 [height][width]; may alias); scratch: gauss_iir_scratch_bytes().  With in_is_rgba8 the input is
 // uchar4 [height][width] whose bytes stand for k/255 (never aliases out).
-void launch_gauss_iir(const void *in, bool in_is_rgba8, float *out, double *scratch, int width, int height, float sigma_h, float sigma_v,
+void launch_gauss_iir_r01(const void *in, bool in_is_rgba8, float *out, double *scratch, int width, int height, float sigma_h, float sigma_v,
                       cudaStream_t stream) {
     GaussCoeffs c;
     // vertical pass: lines are columns (in and out have the same element strides: 4 channels per pixel)
