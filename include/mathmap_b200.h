@@ -76,6 +76,10 @@ int mmb_set_output_bpp(mmb_invocation *inv, int bpp);         /* invocation->out
 int mmb_set_render_size(mmb_invocation *inv, int render_width, int render_height);
 int mmb_set_warp_shape(mmb_invocation *inv, int warp_width); /* pixels per warp row in the 32x8 tile: 32 (default), 16 or 8 */
 int mmb_set_rows_per_thread(mmb_invocation *inv, int rows); /* 32x8 tiles one block renders in sequence (1, 2, 4 or 8; 0 = automatic, the default: up to 8 for straight-line pixel code on large grids, 1 for per-pixel loops, which ignore the setting) */
+/* 1 (default): the pixel kernel of a frame is compiled for the values of the frame-constant conditions it branches on
+ * (`if (userval)`: the reference's init_frame values, new_template.c.in:314-337, as compile-time constants), one NVRTC
+ * compile per combination actually used; 0: one kernel that tests them per pixel */
+int mmb_set_specialize(mmb_invocation *inv, int enabled);
 int mmb_set_precise_math(mmb_invocation *inv, int enabled);   /* 1 (default): libm calls evaluated in double and narrowed, like the host; 0: CUDA float libm (<= 2 ulp, faster) */
 
 /* userval bindings, reference userval.h userval_t / mathmap_cmdline.c:756-796 (-D name=value) */

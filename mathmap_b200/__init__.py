@@ -54,7 +54,7 @@ def lib():
         "mmb_invoke": (vp, [vp, ci, ci, ci]), "mmb_invocation_free": (None, [vp]),
         "mmb_set_antialiasing": (ci, [vp, ci]), "mmb_set_supersampling": (ci, [vp, ci]),
         "mmb_set_edge_behaviour": (ci, [vp, ci, ci, ctypes.c_uint32, ctypes.c_uint32]),
-        "mmb_set_output_bpp": (ci, [vp, ci]), "mmb_set_precise_math": (ci, [vp, ci]), "mmb_set_warp_shape": (ci, [vp, ci]), "mmb_set_rows_per_thread": (ci, [vp, ci]),
+        "mmb_set_output_bpp": (ci, [vp, ci]), "mmb_set_precise_math": (ci, [vp, ci]), "mmb_set_warp_shape": (ci, [vp, ci]), "mmb_set_specialize": (ci, [vp, ci]), "mmb_set_rows_per_thread": (ci, [vp, ci]),
         "mmb_set_userval_int": (ci, [vp, ci, ci]), "mmb_set_userval_float": (ci, [vp, ci, cf]), "mmb_set_userval_bool": (ci, [vp, ci, ci]),
         "mmb_set_userval_color": (ci, [vp, ci, cf, cf, cf, cf]),
         "mmb_set_userval_color_packed": (ci, [vp, ci, ctypes.c_uint32]),
@@ -175,7 +175,8 @@ class Module:
 class Invocation:
     """reference: mathmap_invocation_t from invoke_mathmap (mathmap_common.c:747)."""
 
-    def __init__(self, module, width, height, device=0, antialiasing=False, supersampling=False, precise=True, warp_width=None, rows_per_thread=None):
+    def __init__(self, module, width, height, device=0, antialiasing=False, supersampling=False, precise=True, warp_width=None, rows_per_thread=None,
+                 specialize=None):
         self.module = module
         self.width, self.height = width, height
         self.bpp = 4
@@ -191,6 +192,8 @@ class Invocation:
             self._ck(lib().mmb_set_warp_shape(self._h, warp_width))
         if rows_per_thread is not None:
             self._ck(lib().mmb_set_rows_per_thread(self._h, rows_per_thread))
+        if specialize is not None:
+            self._ck(lib().mmb_set_specialize(self._h, int(specialize)))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

@@ -95,6 +95,8 @@ struct Emitter {
     std::set<const Filter *> &called;  // filters reached through RHS_FILTER
     std::set<const Stmt *> fused;       // statements already emitted as part of a fused pair
     std::string slot_prefix;            // kernels: image uniforms are referenced as the enum constant <slot_prefix><value>
+    std::vector<const Value *> *spec_conds = nullptr;  // the pixel kernel only: frame-constant branch conditions (FilterKernel::spec_conds)
+    std::string cond_prefix;                           // "MM_COND_<filter>_"
 
     Emitter(const mmb_module &m, const FilterCode &c, Mode md, std::set<const Filter *> &cl) : mod(m), code(c), mode(md), call_flavour(md == CALL), called(cl) {}
 
@@ -436,7 +438,18 @@ struct Emitter {
                     emit_stmts(s->alt, ind);
                     break;
                 }
-                out << ind << "if (" << rhs_expr(s->cond, nullptr) << ") {\n";
+                {
+                    std::string cond = rhs_expr(s->cond, nullptr);
+                    const Rhs *c = s->cond;
+                    if (spec_conds && c->kind == RHS_PRIMARY && !c->prim.is_const && c->prim.value->index >= 0 && c->prim.value->level == 0 &&
+                        c->prim.value->cv->type == T_INT) {
+                        size_t n = 0;
+                        while (n < spec_conds->size() && (*spec_conds)[n] != c->prim.value) ++n;
+                        if (n == spec_conds->size()) spec_conds->push_back(c->prim.value);
+                        cond = cond_prefix + std::to_string(n) + "(" + cond + ")";
+                    }
+                    out << ind << "if (" << cond << ") {\n";
+                }
                 emit_stmts(s->cons, ind + "    ");
                 emit_phis(s->exit, 0, ind + "    ");
                 out << ind << "} else {\n";
@@ -538,6 +551,9 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         const bool use_rows = row_cost >= 20;
         Emitter e(m, *code, use_rows ? Emitter::PIXEL_ONLY : Emitter::PIXEL_ALL, called);
         e.slot_prefix = "mm_slot_" + name + "_";
+        std::vector<const Value *> spec_conds;
+        e.spec_conds = &spec_conds;
+        e.cond_prefix = "MM_COND_" + name + "_";
         // body first (discovers uniforms and row exports)
         std::vector<const Value *> decls;
         e.collect_decls(code->first, decls);
@@ -658,6 +674,11 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
 
         std::ostringstream fn;
         fn << st.str() << rv.str();
+        k.spec_conds = spec_conds;
+        k.spec_prefix = "MM_SPEC_" + name + "_";
+        for (size_t i = 0; i < spec_conds.size(); ++i)
+            fn << "#ifdef " << k.spec_prefix << i << "\n#define " << e.cond_prefix << i << "(x) (" << k.spec_prefix << i << ")\n#else\n#define " << e.cond_prefix
+               << i << "(x) (x)\n#endif\n";
         if (have_rows) {
             fn << "extern \"C\" __global__ void __launch_bounds__(256) " << k.row_kernel_name << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
                << name << " U, const __grid_constant__ mm_rowvals_" << name << " RV) {\n"

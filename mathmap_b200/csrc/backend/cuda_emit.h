@@ -35,6 +35,11 @@ struct FilterKernel {
     // is (Blur/Gaussian Blur: `blurred(xy)`).  The invocation may then let the producer of that image write the
     // pixels (invocation.cpp: pass-through).  The uniform whose image is sampled, or null.
     const mm::Value *passthrough_image = nullptr;
+    // Frame-constant values the pixel kernel branches on (`if (userval)`): condition i is MM_COND_<filter>_<i>(U.v...) in
+    // the generated code, which -DMM_SPEC_<filter>_<i>=0|1 turns into a literal, so that NVRTC drops the branch, the
+    // untaken side and the constant load (nvrtc_module.cpp: KernelConfig::spec, invocation.cpp: mmb_init_frame).
+    std::vector<const mm::Value *> spec_conds;
+    std::string spec_prefix;           // "MM_SPEC_<filter>_"
 };
 
 struct CudaModuleSource {

@@ -108,6 +108,7 @@ struct mmb_invocation {
     float t = 0.f;
     bool frame_ready = false;
     FrameData main_frame;
+    std::string main_spec;       // KernelConfig::spec of this frame's launches of the main filter
     int passthrough_image = -1;  // this frame's pixels are the floatmap images[passthrough_image], sampled at their own positions
     std::map<std::string, bool> identity_cache;
     long launches = 0;
@@ -588,7 +589,9 @@ struct LaunchGeom {
 void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, const LaunchGeom &g, void *out, long long out_stride, int floatmap,
                    int frame, float t) {
     std::string err;
-    auto lm = inv->backend->get(inv->cfg, inv->device, err);
+    KernelConfig cfg = inv->cfg;
+    if (f == inv->m->main && cfg.specialize) cfg.spec = inv->main_spec;
+    auto lm = inv->backend->get(cfg, inv->device, err);
     if (!lm) fail(err);
     DriverApi *api = driver_api(err);
     if (!api) fail(err);
@@ -1089,6 +1092,11 @@ int mmb_set_render_size(mmb_invocation *inv, int render_width, int render_height
     inv->frame_ready = false;
     return 0;
 }
+int mmb_set_specialize(mmb_invocation *inv, int enabled) {
+    if (!inv) return -1;
+    inv->cfg.specialize = enabled ? 1 : 0;
+    return 0;
+}
 int mmb_set_warp_shape(mmb_invocation *inv, int warp_width) {
     if (null_inv(inv, "mmb_set_warp_shape")) return -1;
     if (warp_width != 32 && warp_width != 16 && warp_width != 8) { set_error("warp width must be 32, 16 or 8"); return -1; }
@@ -1256,6 +1264,12 @@ int mmb_init_frame(mmb_invocation *inv, int frame, float t) {
                 const HostImage &im = inv->images[it->second.image];
                 if (im.pending_rows && floatmap_lookup_is_identity(inv, im, inv->render_w, inv->render_h)) inv->passthrough_image = it->second.image;
             }
+        }
+        // the frame-constant branch conditions of the pixel kernel, as compile-time constants of this frame's kernel
+        inv->main_spec.clear();
+        for (size_t i = 0; i < mk.spec_conds.size(); ++i) {
+            auto it = rp.env.find(mk.spec_conds[i]);
+            if (it != rp.env.end()) inv->main_spec += "#define " + mk.spec_prefix + std::to_string(i) + (Replay::truth(it->second) ? " 1\n" : " 0\n");
         }
         pack_frame(inv, mk, rp, inv->main_frame);
         inv->frame_ready = true;

@@ -18,6 +18,8 @@ void set_error(const std::string &msg);
 struct KernelConfig {
     int aa = 0, supersampling = 0, edge_x = 0, edge_y = 0, precise = 1, warp_w = 32;
     int rows = 0;  // 32x8 tiles a block renders in sequence (a launch parameter, not part of the key); 0 = chosen per launch
+    int specialize = 1;  // compile the main filter's kernel for the frame-constant branch conditions of the frame (not part of the key)
+    std::string spec;    // "#define MM_SPEC_<filter>_<i> 0|1" lines (FilterKernel::spec_conds), part of the key
     std::string key() const;
 };
 

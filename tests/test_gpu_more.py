@@ -482,3 +482,25 @@ def test_closures_passed_as_images_dispatch_on_the_device():
         want = OracleFilter(m.ir).render(120, 90, {"in": img}, antialiasing=aa)
         exact, le1, mx = compare_u8(got, want)
         assert exact >= 99.9, "aa=%s: %.4f %% exact, %.4f %% within 1 LSB, max %d" % (aa, exact, le1, mx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path,sets", [("examples/Map/Droste.mm", {}), ("examples/Map/Droste.mm", {"NoTransparency": 1, "Strands": 2}),
+                                        ("examples/Distorts/Twirl.mm", {}), ("examples/Blur/Gaussian Blur.mm", {"dev": 0.01})])
+def test_specialised_kernel_equals_generic(path, sets):
+    """the kernel compiled for the frame's branch conditions (mmb_set_specialize, the default) renders the same
+    bytes as the kernel that tests them per pixel, and a change of a boolean userval picks another specialisation."""
+    W, H = 320, 200
+    img = synthetic_rgba(W, H)
+    m = mb.Module(source=filter_source(path))
+    outs = []
+    for spec in (1, 0):
+        inv = mb.Invocation(m, W, H, antialiasing=True, specialize=spec)
+        inv.set("in", img)
+        for k, v in sets.items():
+            inv.set(k, v)
+        outs.append(inv.render(0, 0.3))
+    assert np.array_equal(outs[0], outs[1])
+    want = OracleFilter(m.ir).render(W, H, dict({"in": img}, **sets), t=0.3, antialiasing=True)
+    exact, le1, mx = compare_u8(outs[0], want)
+    assert le1 >= 99.9, (exact, le1, mx)
