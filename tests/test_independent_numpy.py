@@ -1,0 +1,170 @@
+"""a cross-check of the oracle that does not go through the product's front end.
+
+The oracle (oracle/oracle.py) evaluates IR that mathmap_b200's own parser, overload resolution and passes produced, so a
+front-end bug is invisible to every CUDA-vs-oracle test.  Here four filters (the BASELINE configs' Ident, Twirl, Sea and
+Mandelbrot) are evaluated FROM THEIR .mm TEXT BY HAND in numpy float32, following the reference's semantics as SURVEY.md
+Appendix A records them (opmacros.h:156-157 coordinates, mathmap_common.c:59-72 / compiler.c:2339-2420 coordinate systems,
+compiler.c:1710-1773 resize factors, builtins.c:133-245 samplers, builtins.lisp:533-550,732-736,1328-1346 quaternion
+product, norm and polar conversion, new_template.c.in:272-293 quantisation) -- at non-square sizes, t != 0 and with both
+samplers, i.e. away from the reference's own 256x256 goldens.  The oracle must reproduce them bit for bit."""
+import math
+
+import numpy as np
+import pytest
+
+import mathmap_b200 as mb
+from conftest import filter_source, synthetic_rgba
+from oracle.oracle import OracleFilter
+
+F = np.float32
+
+
+def f32(x):
+    return np.asarray(x, dtype=np.float64).astype(np.float32)
+
+
+def libm(fn, *args):
+    """float arguments promoted to double, the double result narrowed"""
+    return fn(*[np.asarray(a, dtype=np.float64) for a in args]).astype(np.float32)
+
+
+def virtual_coords(W, H):
+    cols = np.arange(W, dtype=np.float64)
+    rows = np.arange(H, dtype=np.float64)
+    xu = ((cols - (W - 1) / 2.0) / ((W - 1) / 2.0)).astype(np.float32)
+    yu = ((-rows + (H - 1) / 2.0) / ((H - 1) / 2.0)).astype(np.float32)
+    m = max(W, H)
+    X = F(F(W) / F(m))
+    Y = F(F(H) / F(m))
+    x = (xu * X)[None, :].repeat(H, 0)
+    y = (yu * Y)[:, None].repeat(W, 1)
+    return x.astype(np.float32), y.astype(np.float32), X, Y
+
+
+def sample(img, x, y, bilinear):
+    """origVal on a default-flag image of a default-flag filter: resize factors max/w, max/h, then builtins.c:133-245"""
+    h, w = img.shape[:2]
+    m = max(w, h)
+    x = (x * F(F(m) / F(w))).astype(np.float32)
+    y = (y * F(F(m) / F(h))).astype(np.float32)
+    sx, sy = F((w - 1) / 2.0), F((h - 1) / 2.0)
+    px = ((x + F(1.0)) * sx).astype(np.float32)
+    py = (-((y - F(1.0)) * sy)).astype(np.float32)
+    texels = img.astype(np.float32)
+
+    def texel(ix, iy):
+        inside = (ix >= 0) & (ix < w) & (iy >= 0) & (iy < h)
+        v = texels[np.clip(iy, 0, h - 1), np.clip(ix, 0, w - 1)]
+        return np.where(inside[..., None], v, F(0.0))  # edge colour (0, 0, 0, 0)
+
+    if not bilinear:
+        ix = np.floor((px.astype(np.float64) + 0.5).astype(np.float32)).astype(np.int64)
+        iy = np.floor((py.astype(np.float64) + 0.5).astype(np.float32)).astype(np.int64)
+        q = texel(ix, iy)
+    else:
+        x1 = np.floor(px).astype(np.int64)
+        y1 = np.floor(py).astype(np.int64)
+        x2f = (px - x1.astype(np.float32)).astype(np.float32)
+        y2f = (py - y1.astype(np.float32)).astype(np.float32)
+        x1f = (F(1.0) - x2f).astype(np.float32)
+        y1f = (F(1.0) - y2f).astype(np.float32)
+        p1, p2, p3, p4 = (x1f * y1f)[..., None], (x1f * y2f)[..., None], (x2f * y1f)[..., None], (x2f * y2f)[..., None]
+        c1, c2, c3, c4 = texel(x1, y1), texel(x1, y1 + 1), texel(x1 + 1, y1), texel(x1 + 1, y1 + 1)
+        s = (((c1 * p1).astype(np.float32) + (c2 * p2).astype(np.float32)).astype(np.float32) + (c3 * p3).astype(np.float32)).astype(np.float32)
+        s = (s + (c4 * p4).astype(np.float32)).astype(np.float32)
+        q = np.rint(s)  # round half to even
+    return (q.astype(np.float64) / 255.0).astype(np.float32)
+
+
+def quantise(t):
+    v = np.where(1.0 < t, F(1.0), t)          # MIN(1, t): NaN stays
+    v = np.where(0.0 < v, v, F(0.0))          # MAX(0, v): NaN -> 0
+    return np.floor(v.astype(np.float64) * 255.0).astype(np.uint8)
+
+
+def ident(img, W, H, t, bilinear):
+    x, y, _, _ = virtual_coords(W, H)
+    return quantise(sample(img, x, y, bilinear))
+
+
+def twirl(img, W, H, t, bilinear):
+    """in(ra+ra:[0,(r/R-1)*(t-0.5)*4*pi])"""
+    x, y, _, _ = virtual_coords(W, H)
+    r = libm(np.hypot, x, y)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a = libm(np.arccos, (x / r).astype(np.float32))
+    a = np.where(y < 0, (F(2 * math.pi) - a).astype(np.float32), a)
+    a = np.where(r == 0, F(0.0), a).astype(np.float32)
+    R = F(math.sqrt(2.0))
+    e = ((r / R).astype(np.float32) - F(1.0)).astype(np.float32)
+    e = (e * F(F(t) - F(0.5))).astype(np.float32)
+    e = (e * F(4.0)).astype(np.float32)
+    e = (e * F(math.pi)).astype(np.float32)
+    r2 = (r + F(0.0)).astype(np.float32)
+    a2 = (a + e).astype(np.float32)
+    sx = (libm(np.cos, a2) * r2).astype(np.float32)
+    sy = (libm(np.sin, a2) * r2).astype(np.float32)
+    return quantise(sample(img, sx, sy, bilinear))
+
+
+def sea(img, W, H, t, bilinear, amp1=0.03, amp2=0.01, wv=5.0):
+    """s=sin(t*2*pi+wv*(Y-y+0.1)^-1); in(xy+xy:[amp1*s,amp2*s])"""
+    x, y, _, Y = virtual_coords(W, H)
+    base = ((Y - y).astype(np.float32) + F(0.1)).astype(np.float32)
+    inv = np.where(base == 0, F(0.0), libm(np.power, base, np.full_like(base, -1.0)))  # pow guard: pow(0, b <= 0) = 0
+    arg = ((F(F(t) * F(2.0)) * F(math.pi)).astype(np.float32) + (F(wv) * inv).astype(np.float32)).astype(np.float32)
+    s = libm(np.sin, arg)
+    sx = (x + (F(amp1) * s).astype(np.float32)).astype(np.float32)
+    sy = (y + (F(amp2) * s).astype(np.float32)).astype(np.float32)
+    return quantise(sample(img, sx, sy, bilinear))
+
+
+def mandelbrot(W, H, n_iter):
+    """p = quat:[x, y, 0, 0]; c = quat:[0, 0, 0, 0]; while abs(c) < 2 && iter < n-1: c = c*c + p; gray iter / n"""
+    x, y, _, _ = virtual_coords(W, H)
+    p = [x, y, np.zeros_like(x), np.zeros_like(x)]
+    c = [np.zeros_like(x) for _ in range(4)]
+    it = np.zeros(x.shape, np.int32)
+    m = lambda u, v: (u * v).astype(np.float32)
+    a3 = lambda u, v: (u + v).astype(np.float32)
+    neg = lambda u: (-u).astype(np.float32)
+    for _ in range(n_iter):
+        n2 = a3(a3(a3(m(c[0], c[0]), m(c[1], c[1])), m(c[2], c[2])), m(c[3], c[3]))
+        active = (libm(np.sqrt, n2) < 2) & (it < n_iter - 1)
+        if not active.any():
+            break
+        a, b = c, c
+        q0 = a3(a3(a3(m(a[0], b[0]), neg(m(a[1], b[1]))), neg(m(a[2], b[2]))), neg(m(a[3], b[3])))
+        q1 = a3(a3(a3(m(a[0], b[1]), m(a[1], b[0])), m(a[2], b[3])), neg(m(a[3], b[2])))
+        q2 = a3(a3(a3(m(a[0], b[2]), m(a[2], b[0])), neg(m(a[1], b[3]))), m(a[3], b[1]))
+        q3 = a3(a3(a3(m(a[0], b[3]), m(a[3], b[0])), m(a[1], b[2])), neg(m(a[2], b[1])))
+        new = [a3(q, pp) for q, pp in zip((q0, q1, q2, q3), p)]
+        c = [np.where(active, nv, ov) for nv, ov in zip(new, c)]
+        it = np.where(active, it + 1, it)
+    g = (it.astype(np.float32) / F(n_iter)).astype(np.float32)
+    return quantise(np.stack([g, g, g, np.ones_like(g)], axis=-1))
+
+
+CASES = [("ident", "examples/Utilities/Ident.mm", ident), ("twirl", "examples/Distorts/Twirl.mm", twirl), ("sea", "examples/Distorts/Sea.mm", sea)]
+
+
+@pytest.mark.parametrize("name,path,fn", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("bilinear", [False, True], ids=["nearest", "bilinear"])
+@pytest.mark.parametrize("size,insize,t", [((211, 96), (211, 96), 0.3), ((90, 140), (123, 77), 0.85)])
+def test_oracle_matches_hand_evaluation(name, path, fn, bilinear, size, insize, t):
+    W, H = size
+    img = synthetic_rgba(insize[0], insize[1], seed=7)
+    m = mb.Module(source=filter_source(path))
+    got = OracleFilter(m.ir).render(W, H, {"in": img}, t=t, antialiasing=bilinear)
+    want = fn(img, W, H, t, bilinear)
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert np.array_equal(got, want), "%d pixels differ, max %d" % (int((diff.max(axis=2) > 0).sum()), int(diff.max()))
+
+
+@pytest.mark.parametrize("size,n", [((160, 97), 32), ((75, 120), 100)])
+def test_oracle_matches_hand_evaluation_mandelbrot(size, n):
+    W, H = size
+    m = mb.Module(source=filter_source("examples/Render/Mandelbrot.mm"))
+    got = OracleFilter(m.ir).render(W, H, {"num_iterations": n}, t=0.0)
+    want = mandelbrot(W, H, n)
+    assert np.array_equal(got, want), "%d pixels differ" % int((np.abs(got.astype(int) - want.astype(int)).max(axis=2) > 0).sum())
