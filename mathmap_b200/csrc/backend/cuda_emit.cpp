@@ -95,6 +95,11 @@ struct Emitter {
     std::set<const Filter *> &called;  // filters reached through RHS_FILTER
     std::set<const Stmt *> fused;       // statements already emitted as part of a fused pair
     std::string slot_prefix;            // kernels: image uniforms are referenced as the enum constant <slot_prefix><value>
+    // Quad mode (mm_runtime.cuh: quad kernels): a thread renders four horizontally adjacent pixels.  Per-pixel values
+    // (level 3) are arrays of four, indexed by `qp` while a statement is printed for one of the pixels; qp < 0 at the
+    // top level, where a statement is printed once (row-level values, quad samplers) or four times.
+    bool quad = false;
+    int qp = -1;
     std::vector<const Value *> *spec_conds = nullptr;  // the pixel kernel only: frame-constant branch conditions (FilterKernel::spec_conds)
     std::string cond_prefix;                           // "MM_COND_<filter>_"
 
@@ -111,6 +116,10 @@ struct Emitter {
     }
 
     static std::string vname(const Value *v) { return "v" + std::to_string(v->cv->id) + "_" + std::to_string(v->index); }
+    bool is_vec(const Value *v) const { return quad && v->index >= 0 && v->level >= 3; }
+    // the name of a value of this kernel as an lvalue / rvalue for the pixel being printed
+    std::string ref(const Value *v) const { return is_vec(v) ? vname(v) + "[" + std::to_string(qp < 0 ? 0 : qp) + "]" : vname(v); }
+    std::string pix(const char *name) const { return quad ? std::string(name) + "[" + std::to_string(qp < 0 ? 0 : qp) + "]" : std::string(name); }
     static std::string ctype(const CompVar *cv) {
         switch (cv->type) {
         case T_INT: case T_NIL: return "int";
@@ -151,7 +160,7 @@ struct Emitter {
             }
             unsupported("internal error: value of level " + std::to_string(v->level) + " is not visible here");
         }
-        return vname(v);
+        return ref(v);
     }
     Type ptype(const Primary &p) const { return primary_type(p); }
     std::string as_float(const Primary &p) {
@@ -164,7 +173,8 @@ struct Emitter {
     }
 
     std::string internal(const std::string &n) {
-        if (n == "x" || n == "y" || n == "t" || n == "frame") return n;
+        if (n == "x") return quad ? pix("mm_x") : n;
+        if (n == "y" || n == "t" || n == "frame") return n;
         if (n == "R") return "P.R";
         if (n == "__canvasPixelW") return "P.img_w";
         if (n == "__canvasPixelH") return "P.img_h";
@@ -306,10 +316,10 @@ struct Emitter {
         case OP_ELL_INT_RF: return "mm_ell_int_rf(" + F(0) + ", " + F(1) + ", " + F(2) + ")";
         case OP_ELL_INT_RJ: return "mm_ell_int_rj(" + F(0) + ", " + F(1) + ", " + F(2) + ", " + F(3) + ")";
         case OP_ELL_JAC: return fn2("mm_ell_jac");
-        case OP_RAND: return "mm_rand(mm_rng, " + F(0) + ", " + F(1) + ")";
+        case OP_RAND: return "mm_rand(" + pix("mm_rng") + ", " + F(0) + ", " + F(1) + ")";
         case OP_SOLVE_LINEAR_2: return "mm_solve_linear_2(" + A(0) + ", " + A(1) + ")";
         case OP_SOLVE_LINEAR_3: return "mm_solve_linear_3(" + A(0) + ", " + A(1) + ")";
-        case OP_OUTPUT_TUPLE: return "(mm_ret = " + A(0) + ", 0)";
+        case OP_OUTPUT_TUPLE: return "(" + pix("mm_ret") + " = " + A(0) + ", 0)";
         case OP_STRIP_RESIZE: return A(0);  // device image handles never carry a resize wrapper of their own
         default:
             (void)result_type;
@@ -358,10 +368,12 @@ struct Emitter {
         return false;
     }
 
-    void emit_phis(const Stmt *phis, int branch, const std::string &ind) {
+    // which: 0 every phi, 1 per-pixel (array) phis only, 2 the others only
+    void emit_phis_one(const Stmt *phis, int branch, const std::string &ind, int which) {
         std::vector<const Stmt *> live;
         for (const Stmt *p = phis; p; p = p->next)
             if (p->kind == ST_PHI && on_device(p->lhs->level)) {
+                if ((which == 1 && !is_vec(p->lhs)) || (which == 2 && is_vec(p->lhs))) continue;
                 const Rhs *src = branch == 0 ? p->rhs : p->rhs2;
                 if (src->kind == RHS_PRIMARY && !src->prim.is_const && src->prim.value == p->lhs) continue;
                 live.push_back(p);
@@ -375,15 +387,21 @@ struct Emitter {
                     if (q != p && q->lhs == src->prim.value) hazard = true;
         }
         if (!hazard) {
-            for (const Stmt *p : live) out << ind << vname(p->lhs) << " = " << rhs_expr(branch == 0 ? p->rhs : p->rhs2, p->lhs->cv) << ";\n";
+            for (const Stmt *p : live) out << ind << ref(p->lhs) << " = " << rhs_expr(branch == 0 ? p->rhs : p->rhs2, p->lhs->cv) << ";\n";
             return;
         }
         out << ind << "{\n";
         int k = 0;
         for (const Stmt *p : live) out << ind << "    " << ctype(p->lhs->cv) << " mm_pc" << k++ << " = " << rhs_expr(branch == 0 ? p->rhs : p->rhs2, p->lhs->cv) << ";\n";
         k = 0;
-        for (const Stmt *p : live) out << ind << "    " << vname(p->lhs) << " = mm_pc" << k++ << ";\n";
+        for (const Stmt *p : live) out << ind << "    " << ref(p->lhs) << " = mm_pc" << k++ << ";\n";
         out << ind << "}\n";
+    }
+    void emit_phis(const Stmt *phis, int branch, const std::string &ind) {
+        if (!quad || qp >= 0) { emit_phis_one(phis, branch, ind, 0); return; }
+        emit_phis_one(phis, branch, ind, 2);
+        for (qp = 0; qp < 4; ++qp) emit_phis_one(phis, branch, ind, 1);
+        qp = -1;
     }
 
     // "Direct output": the filter's last two statements are  v = ORIG_VAL(...); OUTPUT_TUPLE(v)  with no other use
@@ -403,33 +421,74 @@ struct Emitter {
         direct_output = last;
     }
 
+    // Can this ORIG_VAL go through a quad sampler?  Printed at the top level of a quad kernel, sample row and frame
+    // shared by the four pixels (the x argument may differ per pixel or not).
+    bool quad_sample(const Stmt *s) const {
+        if (!quad || qp >= 0 || s->kind != ST_ASSIGN || s->rhs->kind != RHS_OP || s->rhs->op->id != OP_ORIG_VAL || !is_vec(s->lhs)) return false;
+        auto scalar = [&](const Primary &p) { return p.is_const || !is_vec(p.value); };
+        const Rhs *r = s->rhs;
+        return scalar(r->args[1]) && scalar(r->args[2]) && scalar(r->args[3]);
+    }
+    // the x arguments of the four pixels as a float[4] initialiser
+    std::string quad_xs(const Primary &x) {
+        std::string l = "{";
+        for (qp = 0; qp < 4; ++qp) l += (qp ? ", " : "") + as_float(x);
+        qp = -1;
+        return l + "}";
+    }
+
+    // one assignment, for the pixel `qp` in quad mode
+    void emit_assign(const Stmt *s, const std::string &ind) {
+        if (s == direct_sample) {
+            const Rhs *r = s->rhs;
+            if (quad)
+                out << ind << "{ bool mm_h; " << ref(s->lhs) << " = mm_orig_val_out(P, " << prim(r->args[2]) << ", " << as_float(r->args[0]) << ", "
+                    << as_float(r->args[1]) << ", " << as_float(r->args[3]) << ", " << pix("mm_word") << ", mm_h); mm_have |= (unsigned)mm_h << " << qp
+                    << "; }\n";
+            else
+                out << ind << vname(s->lhs) << " = mm_orig_val_out(P, " << prim(r->args[2]) << ", " << as_float(r->args[0]) << ", "
+                    << as_float(r->args[1]) << ", " << as_float(r->args[3]) << ", mm_word, mm_have_word);\n";
+            return;
+        }
+        // sin(v) and cos(v) of the same value in one block share one range reduction
+        if (s->rhs->kind == RHS_OP && (s->rhs->op->id == OP_SIN || s->rhs->op->id == OP_COS) && s->lhs->cv->type == T_FLOAT) {
+            const int other = s->rhs->op->id == OP_SIN ? OP_COS : OP_SIN;
+            const Stmt *mate = nullptr;
+            for (const Stmt *q = s->next; q; q = q->next)
+                if (q->kind == ST_ASSIGN && q->rhs->kind == RHS_OP && q->rhs->op->id == other && on_device(q->lhs->level) &&
+                    q->lhs->cv->type == T_FLOAT && !q->rhs->args[0].is_const && !s->rhs->args[0].is_const &&
+                    q->rhs->args[0].value == s->rhs->args[0].value && is_vec(q->lhs) == is_vec(s->lhs)) { mate = q; break; }
+            if (mate) {
+                fused.insert(mate);
+                const Stmt *sn = s->rhs->op->id == OP_SIN ? s : mate, *cs = s->rhs->op->id == OP_SIN ? mate : s;
+                out << ind << "mm_sincos(" << as_float(s->rhs->args[0]) << ", " << ref(sn->lhs) << ", " << ref(cs->lhs) << ");\n";
+                return;
+            }
+        }
+        out << ind << ref(s->lhs) << " = " << rhs_expr(s->rhs, s->lhs->cv) << ";\n";
+    }
+
     void emit_stmts(const Stmt *s, const std::string &ind) {
         for (; s; s = s->next) {
             switch (s->kind) {
             case ST_ASSIGN:
                 if (!on_device(s->lhs->level) || fused.count(s)) break;
-                if (s == direct_sample) {
+                if (quad_sample(s)) {
                     const Rhs *r = s->rhs;
-                    out << ind << vname(s->lhs) << " = mm_orig_val_out(P, " << prim(r->args[2]) << ", " << as_float(r->args[0]) << ", "
-                        << as_float(r->args[1]) << ", " << as_float(r->args[3]) << ", mm_word, mm_have_word);\n";
+                    out << ind << "{ const float mm_qx[4] = " << quad_xs(r->args[0]) << "; ";
+                    if (s == direct_sample)
+                        out << "mm_orig_val_out_quad(P, " << prim(r->args[2]) << ", mm_qx, " << as_float(r->args[1]) << ", " << as_float(r->args[3]) << ", "
+                            << vname(s->lhs) << ", mm_word, mm_have); }\n";
+                    else
+                        out << "mm_orig_val_quad(P, " << prim(r->args[2]) << ", mm_qx, " << as_float(r->args[1]) << ", " << as_float(r->args[3]) << ", "
+                            << vname(s->lhs) << "); }\n";
                     break;
                 }
-                // sin(v) and cos(v) of the same value in one block share one range reduction
-                if (s->rhs->kind == RHS_OP && (s->rhs->op->id == OP_SIN || s->rhs->op->id == OP_COS) && s->lhs->cv->type == T_FLOAT) {
-                    const int other = s->rhs->op->id == OP_SIN ? OP_COS : OP_SIN;
-                    const Stmt *mate = nullptr;
-                    for (const Stmt *q = s->next; q; q = q->next)
-                        if (q->kind == ST_ASSIGN && q->rhs->kind == RHS_OP && q->rhs->op->id == other && on_device(q->lhs->level) &&
-                            q->lhs->cv->type == T_FLOAT && !q->rhs->args[0].is_const && !s->rhs->args[0].is_const &&
-                            q->rhs->args[0].value == s->rhs->args[0].value) { mate = q; break; }
-                    if (mate) {
-                        fused.insert(mate);
-                        const Stmt *sn = s->rhs->op->id == OP_SIN ? s : mate, *cs = s->rhs->op->id == OP_SIN ? mate : s;
-                        out << ind << "mm_sincos(" << as_float(s->rhs->args[0]) << ", " << vname(sn->lhs) << ", " << vname(cs->lhs) << ");\n";
-                        break;
-                    }
-                }
-                out << ind << vname(s->lhs) << " = " << rhs_expr(s->rhs, s->lhs->cv) << ";\n";
+                if (quad && qp < 0 && is_vec(s->lhs)) {
+                    for (qp = 0; qp < 4; ++qp) emit_assign(s, ind);
+                    qp = -1;
+                } else
+                    emit_assign(s, ind);
                 break;
             case ST_IF:
                 if (!(has_device(s->cons) || has_device(s->alt) || has_device(s->exit))) break;
@@ -438,24 +497,11 @@ struct Emitter {
                     emit_stmts(s->alt, ind);
                     break;
                 }
-                {
-                    std::string cond = rhs_expr(s->cond, nullptr);
-                    const Rhs *c = s->cond;
-                    if (spec_conds && c->kind == RHS_PRIMARY && !c->prim.is_const && c->prim.value->index >= 0 && c->prim.value->level == 0 &&
-                        c->prim.value->cv->type == T_INT) {
-                        size_t n = 0;
-                        while (n < spec_conds->size() && (*spec_conds)[n] != c->prim.value) ++n;
-                        if (n == spec_conds->size()) spec_conds->push_back(c->prim.value);
-                        cond = cond_prefix + std::to_string(n) + "(" + cond + ")";
-                    }
-                    out << ind << "if (" << cond << ") {\n";
-                }
-                emit_stmts(s->cons, ind + "    ");
-                emit_phis(s->exit, 0, ind + "    ");
-                out << ind << "} else {\n";
-                emit_stmts(s->alt, ind + "    ");
-                emit_phis(s->exit, 1, ind + "    ");
-                out << ind << "}\n";
+                if (quad && qp < 0 && s->level >= 3) {  // a per-pixel condition: the whole construct once per pixel
+                    for (qp = 0; qp < 4; ++qp) emit_if(s, ind);
+                    qp = -1;
+                } else
+                    emit_if(s, ind);
                 break;
             case ST_WHILE:
                 if (!on_device(s->level)) {
@@ -472,6 +518,24 @@ struct Emitter {
             default: break;
             }
         }
+    }
+    void emit_if(const Stmt *s, const std::string &ind) {
+        std::string cond = rhs_expr(s->cond, nullptr);
+        const Rhs *c = s->cond;
+        if (spec_conds && c->kind == RHS_PRIMARY && !c->prim.is_const && c->prim.value->index >= 0 && c->prim.value->level == 0 &&
+            c->prim.value->cv->type == T_INT) {
+            size_t n = 0;
+            while (n < spec_conds->size() && (*spec_conds)[n] != c->prim.value) ++n;
+            if (n == spec_conds->size()) spec_conds->push_back(c->prim.value);
+            cond = cond_prefix + std::to_string(n) + "(" + cond + ")";
+        }
+        out << ind << "if (" << cond << ") {\n";
+        emit_stmts(s->cons, ind + "    ");
+        emit_phis(s->exit, 0, ind + "    ");
+        out << ind << "} else {\n";
+        emit_stmts(s->alt, ind + "    ");
+        emit_phis(s->exit, 1, ind + "    ");
+        out << ind << "}\n";
     }
 
     void collect_decls(const Stmt *s, std::vector<const Value *> &vals) const {
@@ -549,7 +613,32 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
             scan(code->first);
         }
         const bool use_rows = row_cost >= 20;
+        // Quad kernel (four pixels of a row per thread, mm_runtime.cuh): for straight-line pixel code with at least one
+        // sample whose row and frame do not depend on the column -- in(xy), translations, scalings, stencils with
+        // constant offsets ... (the reference's "y-const" values, compiler.c:2867-3234, new_template.c.in:339-373)
+        bool quad = false;
+        {
+            std::function<bool(const Stmt *)> has_pixel_loop = [&](const Stmt *st) {
+                for (; st; st = st->next) {
+                    if (st->kind == ST_WHILE && st->level >= 1) return true;
+                    if (st->kind == ST_IF && (has_pixel_loop(st->cons) || has_pixel_loop(st->alt))) return true;
+                }
+                return false;
+            };
+            std::function<bool(const Stmt *)> has_row_sample = [&](const Stmt *st) {
+                for (; st; st = st->next) {
+                    if (st->kind == ST_ASSIGN && st->rhs->kind == RHS_OP && st->rhs->op->id == OP_ORIG_VAL && st->lhs->level >= 3) {
+                        auto below = [](const Primary &q, int l) { return q.is_const || q.value->index < 0 || q.value->level < l; };
+                        if (below(st->rhs->args[1], 3) && below(st->rhs->args[2], 1) && below(st->rhs->args[3], 3)) return true;
+                    } else if (st->kind == ST_IF && st->level < 3 && (has_row_sample(st->cons) || has_row_sample(st->alt)))
+                        return true;
+                }
+                return false;
+            };
+            quad = !has_pixel_loop(code->first) && has_row_sample(code->first);
+        }
         Emitter e(m, *code, use_rows ? Emitter::PIXEL_ONLY : Emitter::PIXEL_ALL, called);
+        e.quad = quad;
         e.slot_prefix = "mm_slot_" + name + "_";
         std::vector<const Value *> spec_conds;
         e.spec_conds = &spec_conds;
@@ -691,15 +780,25 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
             for (const Value *v : row_decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
             fn << row_body << rv_store.str() << "}\n";
         }
+        k.quad = quad;
         fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H) " << k.kernel_name << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
            << name << " U, const __grid_constant__ mm_rowvals_" << name << " RV) {\n"
            << "    int col, mm_row0;\n"
-           << (k.auto_rows > 1 ? "    const int mm_rows = P.rows;\n" : "    constexpr int mm_rows = 1;  // per-pixel loops: one tile per block\n")
-           << "    mm_pixel_coords(col, mm_row0, mm_rows);\n"
-           << "    if (col >= P.region_w) return;\n"
-           << "    const float x = __ldg(P.xs + (col + P.region_x));\n"
-           << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)x;\n"
-           << "    // tile k of this block: compact row mm_row0 + 8 k, absolute row mm_arow0 + k * mm_astep (8-row blocks may be interleaved over\n"
+           << (k.auto_rows > 1 ? "    const int mm_rows = P.rows;\n" : "    constexpr int mm_rows = 1;  // per-pixel loops: one tile per block\n");
+        if (quad)
+            fn << "    mm_pixel_coords_quad(col, mm_row0, mm_rows);  // columns col .. col+3\n"
+               << "    if (col >= P.region_w) return;\n"
+               << "    const int mm_np = P.region_w - col < 4 ? P.region_w - col : 4;  // pixels of the strip inside the region\n"
+               << "    float mm_x[4];\n"
+               << "#pragma unroll\n"
+               << "    for (int mm_p = 0; mm_p < 4; ++mm_p) mm_x[mm_p] = __ldg(P.xs + ((mm_p < mm_np ? col + mm_p : col + mm_np - 1) + P.region_x));\n"
+               << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)mm_x;\n";
+        else
+            fn << "    mm_pixel_coords(col, mm_row0, mm_rows);\n"
+               << "    if (col >= P.region_w) return;\n"
+               << "    const float x = __ldg(P.xs + (col + P.region_x));\n"
+               << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)x;\n";
+        fn << "    // tile k of this block: compact row mm_row0 + 8 k, absolute row mm_arow0 + k * mm_astep (8-row blocks may be interleaved over\n"
            << "    // ranks), output row pointer advancing by 8 rows -- all loop-invariant work is done here, once\n"
            << "    const int mm_arow0 = mm_actual_row(P, mm_row0), mm_astep = MM_BLOCK_H * (P.row_interleave > 1 ? P.row_interleave : 1);\n"
            << "    char *mm_outp = (char *)P.out + (size_t)mm_row0 * (size_t)P.out_stride;\n"
@@ -710,28 +809,25 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
            << "    if (row >= P.num_rows) return;\n"
            << "    const int arow = mm_arow0 + mm_rep * mm_astep;\n"
            << "    if (arow >= P.row_limit) return;\n"
-           << "    const float y = __ldg(P.ys + arow); (void)y;\n"
-           << "    mm_tup<4> mm_ret = mm_tup<4>{};\n"
-           << "    unsigned mm_rng = mm_rng_seed(col + P.region_x, arow, P.frame); (void)mm_rng;\n";
+           << "    const float y = __ldg(P.ys + arow); (void)y;\n";
+        if (quad)
+            fn << "    mm_tup<4> mm_ret[4] = {};\n"
+               << "    unsigned mm_rng[4];\n"
+               << "#pragma unroll\n"
+               << "    for (int mm_p = 0; mm_p < 4; ++mm_p) mm_rng[mm_p] = mm_rng_seed(col + mm_p + P.region_x, arow, P.frame);\n"
+               << "    (void)mm_rng;\n";
+        else
+            fn << "    mm_tup<4> mm_ret = mm_tup<4>{};\n"
+               << "    unsigned mm_rng = mm_rng_seed(col + P.region_x, arow, P.frame); (void)mm_rng;\n";
         if (have_rows) fn << rv_load.str();
-        if (e.direct_sample) fn << "    unsigned mm_word = 0; bool mm_have_word = false;\n";
-        for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
-        if (e.direct_sample) {
-            // img(xy) with x, y the pixel's own coordinates and a frame-constant image and frame
-            const Rhs *r = e.direct_sample->rhs;
-            auto internal_is = [](const Primary &p, const char *name) {
-                return !p.is_const && p.value->index >= 0 && p.value->def && p.value->def->kind == ST_ASSIGN && p.value->def->rhs->kind == RHS_INTERNAL &&
-                       p.value->def->rhs->internal == name;
-            };
-            const Primary &im = r->args[2], &tt = r->args[3];
-            if (internal_is(r->args[0], "x") && internal_is(r->args[1], "y") && !im.is_const && im.value->index >= 0 && im.value->level == 0 &&
-                (tt.is_const || tt.value->index < 0 || tt.value->level == 0))
-                k.passthrough_image = im.value;
-        }
-        fn << body
-           << (e.direct_sample ? "    if (mm_have_word) mm_store_word(mm_outp, col, mm_word); else\n" : "")
-           << "    mm_store_pixel(P, mm_outp, col, mm_ret);\n"
-           << "    }\n}\n";
+        if (quad) fn << "    unsigned mm_word[4] = {0, 0, 0, 0}, mm_have = 0; (void)mm_word;\n";
+        else if (e.direct_sample) fn << "    unsigned mm_word = 0; bool mm_have_word = false;\n";
+        for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << (e.is_vec(v) ? "[4]" : "") << ";\n";
+        fn << body;
+        if (quad) fn << "    mm_store_quad(P, mm_outp, col, mm_np, mm_ret, mm_word, mm_have);\n";
+        else
+            fn << (e.direct_sample ? "    if (mm_have_word) mm_store_word(mm_outp, col, mm_word); else\n" : "") << "    mm_store_pixel(P, mm_outp, col, mm_ret);\n";
+        fn << "    }\n}\n";
         if (closure_fn) {  // new_template.c.in:375-422 filter_$name, with the frame constants precomputed
             fn << "__device__ mm_tup<4> mm_closure_" << name << "(const mm_params &P, const mm_uniforms_" << name << " &U, float x, float y, float t) {\n"
                << "    const int frame = 0;\n    (void)frame; (void)x; (void)y; (void)t;\n    mm_tup<4> mm_ret = mm_tup<4>{};\n"

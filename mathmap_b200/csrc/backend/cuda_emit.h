@@ -31,6 +31,7 @@ struct FilterKernel {
     int filter_index = -1;             // position in the module's filter list: mm_image::closure_filter of its closures
     bool closure_fn = false;           // a device function mm_closure_<f> exists (the filter occurs as a closure value)
     int auto_rows = 1;                 // the most 32x8 tiles a block renders in sequence (1 for kernels with per-pixel loops)
+    bool quad = false;                 // a thread renders 4 adjacent pixels of a row: tiles are 128 x 8 pixels (mm_runtime.cuh: quad kernels)
     // The filter's pixel is `img(xy)`: ORIG_VAL of a frame-constant image at the pixel's own coordinates, output as it
     // is (Blur/Gaussian Blur: `blurred(xy)`).  The invocation may then let the producer of that image write the
     // pixels (invocation.cpp: pass-through).  The uniform whose image is sampled, or null.

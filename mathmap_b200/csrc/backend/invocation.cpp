@@ -618,13 +618,18 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     P.floatmap = floatmap;
     P.out_mode = floatmap ? 1 : (inv->bpp == 4 ? 0 : 2);
     P.magic23 = 0x4B000000u;
+    P.pk_neg_zero = 0x8000000080000000ull;
+    P.pk_one = 0x3f8000003f800000ull;
+    P.pk_magic_round = 0x4b4000004b400000ull;
     P.edge_color_x = inv->edge_color_x;
     P.edge_color_y = inv->edge_color_y;
     for (int i = 0; i < fd.nslots; ++i) P.images[i] = fd.slots[i];
     // row pre-kernel: row-constant values are computed once per row into 4-byte arrays the pixel kernel reads
     std::vector<void *> rowvals((size_t)std::max(1, k.row_slots), nullptr);
     void *params[3] = {&P, (void *)fd.uniforms.data(), (void *)rowvals.data()};
-    unsigned gx = (unsigned)((g.region_w + 31) / 32), gy;
+    const int tile_w = k.quad ? 128 : 32;
+    unsigned gx = (unsigned)((g.region_w + tile_w - 1) / tile_w), gy;
+    P.vec_store = ((uintptr_t)out & 15) == 0 && (out_stride & 15) == 0;
     {
         // Tiles per block: as many as the kernel takes (k.auto_rows) while the grid still has about six waves of
         // blocks (8 resident blocks per SM), so that the tail of a small frame stays short.  Measured at 8192^2 for

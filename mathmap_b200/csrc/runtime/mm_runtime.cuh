@@ -604,6 +604,56 @@ MM_DEV float mm_unit_from_rounded(float qf) {  // qf holds an integer 0..255 exa
 // an integer, and subtracting 2^23 again (exact) gives floor(v) as a float -- no conversion instructions
 MM_DEV float mm_floor_biased(float v) { return __fadd_rd(v, 8388608.0f); }
 
+// ---- packed FP32 arithmetic (Blackwell FFMA2: two floats per lane and issue slot) -----------------------------------
+// The blend of a bilinear sample is 7 multiply / add operations per channel, each rounded on its own.  On two channels
+// at once it takes half the issue slots, which is what bounds the sampling kernels.  ptxas contracts mul.f32x2 +
+// add.f32x2 into FFMA2 whatever --fmad says (and rewrites fma(a, b, -0) / fma(s, 1, m) to get there), which would round
+// once instead of twice; so the product is written fma(a, b, NZ) and the sum fma(s, ONE, m) with NZ = (-0, -0) and
+// ONE = (1, 1) arriving as kernel DATA (mm_params): a*b + (-0) is RN(a*b) for every a, b including the sign of a zero
+// product, s*1 + m is RN(s + m), and two FMAs cannot be fused or simplified when their constants are not known.
+MM_DEV unsigned long long mm_pk(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+MM_DEV void mm_unpk(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+MM_DEV unsigned long long mm_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// ((a*p1 + b*p2) + c*p3) + d*p4 + 1.5*2^23 on a pair of channels, every product and sum rounded to float
+MM_DEV unsigned long long mm_blend2(const mm_params &P, unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d,
+                                    unsigned long long p1, unsigned long long p2, unsigned long long p3, unsigned long long p4) {
+    const unsigned long long nz = P.pk_neg_zero, one = P.pk_one;
+    unsigned long long s = mm_fma2(mm_fma2(a, p1, nz), one, mm_fma2(b, p2, nz));
+    s = mm_fma2(s, one, mm_fma2(c, p3, nz));
+    s = mm_fma2(s, one, mm_fma2(d, p4, nz));
+    return mm_fma2(s, one, P.pk_magic_round);
+}
+
+MM_DEV void mm_texel_floats(unsigned word, unsigned magic, float (&c)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = mm_texel_channel(word, magic, k);
+}
+// One pixel from its four texels' channel floats (a = (x1,y1), b = (x1,y2), c = (x2,y1), d = (x2,y2)) and weights:
+// per channel ((a*p1 + b*p2) + c*p3) + d*p4, then rintf through the 1.5 * 2^23 constant (round half to even, exact for
+// 0..255: the low mantissa byte of the biased sum is (int)rintf(s) & 0xff), on two channels per instruction.
+template <bool WORD>
+MM_DEV void mm_blend_texels(const mm_params &P, const float (&a)[4], const float (&b)[4], const float (&c)[4], const float (&d)[4], float p1, float p2,
+                            float p3, float p4, mm_tup<4> &out, unsigned &word) {
+    const unsigned long long w1 = mm_pk(p1, p1), w2 = mm_pk(p2, p2), w3 = mm_pk(p3, p3), w4 = mm_pk(p4, p4);
+    float biased[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        mm_unpk(mm_blend2(P, mm_pk(a[2 * h], a[2 * h + 1]), mm_pk(b[2 * h], b[2 * h + 1]), mm_pk(c[2 * h], c[2 * h + 1]), mm_pk(d[2 * h], d[2 * h + 1]), w1, w2,
+                          w3, w4),
+                biased[2 * h], biased[2 * h + 1]);
+    if (WORD)
+        word = __byte_perm(__byte_perm((unsigned)__float_as_int(biased[0]), (unsigned)__float_as_int(biased[1]), 0x0040),
+                           __byte_perm((unsigned)__float_as_int(biased[2]), (unsigned)__float_as_int(biased[3]), 0x0040), 0x5410);
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out.v[k] = mm_unit_from_rounded(__fsub_rn(biased[k], MM_MAGIC_ROUND));
+    }
+}
+
 // WORD: instead of the four channel floats k/255, return the rounded bytes k themselves as one RGBA8 word in memory
 // order (the direct-output case, see mm_orig_val_out).
 template <bool WORD> MM_DEV bool mm_bilinear_interior(const mm_params &P, const mm_image &img, float x, float y, float t, mm_tup<4> &out, unsigned &word) {
@@ -623,17 +673,12 @@ template <bool WORD> MM_DEV bool mm_bilinear_interior(const mm_params &P, const 
     const unsigned *row1 = row0 + img.w;
     const unsigned t1 = __ldg(row0), t3 = __ldg(row0 + 1), t2 = __ldg(row1), t4 = __ldg(row1 + 1);  // pixel1..4 of builtins.c:221-224
     const unsigned magic = P.magic23;
-    unsigned q[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {  // memory byte k is R, G, B, A
-        const float a = mm_texel_channel(t1, magic, k), b = mm_texel_channel(t2, magic, k), c = mm_texel_channel(t3, magic, k),
-                    d = mm_texel_channel(t4, magic, k);
-        const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, p1), __fmul_rn(b, p2)), __fmul_rn(c, p3)), __fmul_rn(d, p4));
-        const float biased = __fadd_rn(s, MM_MAGIC_ROUND);  // 1.5 * 2^23 + rintf(s), 0 <= s < 256: the low mantissa byte is (int)rintf(s) & 0xff
-        if (WORD) q[k] = (unsigned)__float_as_int(biased);
-        else out.v[k] = mm_unit_from_rounded(__fsub_rn(biased, MM_MAGIC_ROUND));
-    }
-    if (WORD) word = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+    float a[4], b[4], c[4], d[4];  // memory byte k is R, G, B, A
+    mm_texel_floats(t1, magic, a);
+    mm_texel_floats(t2, magic, b);
+    mm_texel_floats(t3, magic, c);
+    mm_texel_floats(t4, magic, d);
+    mm_blend_texels<WORD>(P, a, b, c, d, p1, p2, p3, p4, out, word);
     return true;
 #else
     return false;
@@ -760,6 +805,165 @@ MM_DEV mm_tup<4> mm_orig_val_out(const mm_params &P, int image, float x, float y
     return mm_orig_val_call(P, image, x, y, t);
 }
 
+// ---- quad kernels: four horizontally adjacent pixels of one row per thread ---------------------------------------
+// The "local access" variant of the pixel kernel (cuda_emit.cpp: quad mode), for filters whose samples are separable:
+// the sample's x depends on the column only and its y on the row only (in(xy), translations, scalings, zooms, flips,
+// stencils with constant offsets, everything that then only works on the colour).  The reference computes what
+// depends on the column once per slice (init_slice, new_template.c.in:339-373); here a thread renders a 4 x 1 strip, so
+// that per sample
+//   * the row half of the work (coordinate transform, floor, weights, row addresses) is done once for four pixels,
+//   * neighbouring pixels whose texel columns are consecutive (x1(p+1) == x1(p) + 1: the common case at unit scale)
+//     share texels: 10 loads and byte -> float conversions of 40 channels instead of 16 and 64,
+//   * the four RGBA8 results leave as one 128-bit store.
+// Results are bit-identical to the one-pixel samplers: the same float operations per pixel, in the same order.
+MM_DEV void mm_pixel_coords_quad(int &col, int &row, int rows) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    col = (blockIdx.x * MM_BLOCK_W + lane) * 4;
+    row = blockIdx.y * (MM_BLOCK_H * rows) + warp;
+}
+// Returns 0xf when all four samples lie in the image's interior and were taken here, else 0 (the caller then takes the
+// pixels one by one through the general sampler: border strips only).
+template <bool WORD>
+MM_DEV unsigned mm_bilinear_quad(const mm_params &P, const mm_image &img, const float (&x)[4], float y, float t, mm_tup<4> (&out)[4], unsigned (&word)[4]) {
+#if MM_EDGE_X == 0 && MM_EDGE_Y == 0
+    const float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
+    if (!(py >= 0.0f && py < img.fast_hm1 && t > -1.0f && t < img.fast_nf)) return 0u;
+    float px[4];
+    bool inside = true;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        px[p] = __fmul_rn(__fadd_rn(x[p], img.mx), img.sx);
+        inside = inside && px[p] >= 0.0f && px[p] < img.fast_wm1;
+    }
+    if (!inside) return 0u;
+    const float by = mm_floor_biased(py), fy = __fsub_rn(by, 8388608.0f);
+    const float y2f = __fsub_rn(py, fy), y1f = __fsub_rn(1.0f, y2f);
+    const unsigned *row0 = img.fast_base + ((unsigned)__float_as_int(by) & 0x7fffffu) * (unsigned)img.w;
+    const unsigned *row1 = row0 + img.w;
+    const unsigned magic = P.magic23;
+    float bx[4], x2f[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        bx[p] = mm_floor_biased(px[p]);
+        x2f[p] = __fsub_rn(px[p], __fsub_rn(bx[p], 8388608.0f));
+    }
+    const unsigned i0 = (unsigned)__float_as_int(bx[0]);
+    // Decided per warp: where the lanes disagree (at unit scale floor(px) is the column or the one before it, as the float
+    // rounding of px falls) a warp would run both variants.
+    const bool consecutive = (unsigned)__float_as_int(bx[1]) == i0 + 1 && (unsigned)__float_as_int(bx[2]) == i0 + 2 && (unsigned)__float_as_int(bx[3]) == i0 + 3;
+    if (__all_sync(__activemask(), consecutive)) {
+        // consecutive texel columns: pixel p blends columns p and p + 1 of five
+        unsigned ta[5], tb[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { ta[j] = __ldg(row0 + i0 + j); tb[j] = __ldg(row1 + i0 + j); }
+        float la[4], lb[4];
+        mm_texel_floats(ta[0], magic, la);
+        mm_texel_floats(tb[0], magic, lb);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float ra[4], rb[4];
+            mm_texel_floats(ta[p + 1], magic, ra);
+            mm_texel_floats(tb[p + 1], magic, rb);
+            const float x1f = __fsub_rn(1.0f, x2f[p]);
+            mm_blend_texels<WORD>(P, la, lb, ra, rb, __fmul_rn(x1f, y1f), __fmul_rn(x1f, y2f), __fmul_rn(x2f[p], y1f), __fmul_rn(x2f[p], y2f), out[p], word[p]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { la[k] = ra[k]; lb[k] = rb[k]; }
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const unsigned ix = (unsigned)__float_as_int(bx[p]);
+            float a[4], b[4], c[4], d[4];
+            mm_texel_floats(__ldg(row0 + ix), magic, a);
+            mm_texel_floats(__ldg(row1 + ix), magic, b);
+            mm_texel_floats(__ldg(row0 + ix + 1), magic, c);
+            mm_texel_floats(__ldg(row1 + ix + 1), magic, d);
+            const float x1f = __fsub_rn(1.0f, x2f[p]);
+            mm_blend_texels<WORD>(P, a, b, c, d, __fmul_rn(x1f, y1f), __fmul_rn(x1f, y2f), __fmul_rn(x2f[p], y1f), __fmul_rn(x2f[p], y2f), out[p], word[p]);
+        }
+    }
+    return 0xfu;
+#else
+    return 0u;
+#endif
+}
+template <bool WORD>
+MM_DEV unsigned mm_nearest_quad(const mm_params &P, const mm_image &img, const float (&x)[4], float y, float t, mm_tup<4> (&out)[4], unsigned (&word)[4]) {
+#if MM_EDGE_X == 0 && MM_EDGE_Y == 0
+    float py = -__fmul_rn(__fsub_rn(y, img.my), img.sy);
+#if !MM_SUPERSAMPLING
+    py = __fadd_rn(py, 0.5f);
+#endif
+    if (!(py >= 0.0f && py < img.fast_h && t > -1.0f && t < img.fast_nf)) return 0u;
+    float px[4];
+    bool inside = true;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        px[p] = __fmul_rn(__fadd_rn(x[p], img.mx), img.sx);
+#if !MM_SUPERSAMPLING
+        px[p] = __fadd_rn(px[p], 0.5f);
+#endif
+        inside = inside && px[p] >= 0.0f && px[p] < img.fast_w;
+    }
+    if (!inside) return 0u;
+    const unsigned *row = img.fast_base + ((unsigned)__float_as_int(mm_floor_biased(py)) & 0x7fffffu) * (unsigned)img.w;
+    const unsigned magic = P.magic23;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const unsigned texel = __ldg(row + (unsigned)__float_as_int(mm_floor_biased(px[p])));
+        if (WORD) word[p] = texel;
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[p].v[k] = mm_unit_from_rounded(mm_texel_channel(texel, magic, k));
+        }
+    }
+    return 0xfu;
+#else
+    return 0u;
+#endif
+}
+// ORIG_VAL of four pixels of a row whose sample rows coincide (y, t shared)
+MM_DEV void mm_orig_val_quad(const mm_params &P, int image, const float (&x)[4], float y, float t, mm_tup<4> (&r)[4]) {
+    const mm_image &img = P.images[image];
+    unsigned done = 0u;
+    if (img.kind == MM_IMAGE_DRAWABLE) {
+        float xs[4];
+        unsigned unused[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) xs[p] = __fmul_rn(x[p], img.xf);
+#if MM_AA
+        done = mm_bilinear_quad<false>(P, img, xs, __fmul_rn(y, img.yf), t, r, unused);
+#else
+        done = mm_nearest_quad<false>(P, img, xs, __fmul_rn(y, img.yf), t, r, unused);
+#endif
+    }
+    if (done != 0xfu) {  // unrolled: a runtime index would put the arrays into local memory
+#pragma unroll
+        for (int p = 0; p < 4; ++p) r[p] = mm_orig_val_call(P, image, x[p], y, t);
+    }
+}
+// ... whose results are the pixels themselves (see mm_orig_val_out): `have` gets a bit per pixel whose RGBA8 word is in `word`
+MM_DEV void mm_orig_val_out_quad(const mm_params &P, int image, const float (&x)[4], float y, float t, mm_tup<4> (&r)[4], unsigned (&word)[4], unsigned &have) {
+    const mm_image &img = P.images[image];
+    have = 0u;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) r[p] = mm_tup<4>{};
+    if (P.out_mode == 0 && img.kind == MM_IMAGE_DRAWABLE) {
+        float xs[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) xs[p] = __fmul_rn(x[p], img.xf);
+#if MM_AA
+        have = mm_bilinear_quad<true>(P, img, xs, __fmul_rn(y, img.yf), t, r, word);
+#else
+        have = mm_nearest_quad<true>(P, img, xs, __fmul_rn(y, img.yf), t, r, word);
+#endif
+    }
+    if (have != 0xfu) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) r[p] = mm_orig_val_call(P, image, x[p], y, t);
+    }
+}
+
 // local (compact) row of this launch -> absolute image row
 MM_DEV int mm_actual_row(const mm_params &P, int row) {
     if (P.row_interleave <= 1) return row + P.first_row;
@@ -794,6 +998,29 @@ MM_DEV void mm_store_pixel(const mm_params &P, char *rowp, int col, const mm_tup
         p[0] = (unsigned char)mm_d2i(l);
         if (P.bpp == 2) p[1] = mm_quant(t.v[3]);
     }
+}
+
+// the RGBA8 word of a pixel (the out_mode 0 branch of mm_store_pixel)
+MM_DEV unsigned mm_pack_pixel(const mm_tup<4> &t) {
+    const unsigned rg = __byte_perm(mm_quant_bits(t.v[0]), mm_quant_bits(t.v[1]), 0x0040);
+    const unsigned ba = __byte_perm(mm_quant_bits(t.v[2]), mm_quant_bits(t.v[3]), 0x0040);
+    return __byte_perm(rg, ba, 0x5410);
+}
+// np of the four pixels from column col on lie inside the region; `have`: pixels whose word is already in `word`
+MM_DEV void mm_store_quad(const mm_params &P, char *rowp, int col, int np, const mm_tup<4> (&t)[4], const unsigned (&word)[4], unsigned have) {
+    if (P.out_mode == 0) {
+        unsigned w[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) w[p] = ((have >> p) & 1u) ? word[p] : mm_pack_pixel(t[p]);
+        if (np == 4 && P.vec_store) { *(uint4 *)(rowp + (size_t)col * 4) = make_uint4(w[0], w[1], w[2], w[3]); return; }
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if (p < np) ((unsigned *)rowp)[col + p] = w[p];
+        return;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        if (p < np) mm_store_pixel(P, rowp, col + p, t[p]);
 }
 
 #include "mm_noise.cuh"

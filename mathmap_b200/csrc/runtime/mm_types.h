@@ -48,6 +48,9 @@ struct mm_params {
     int out_mode;             // 0: RGBA8 (bpp 4), 1: floatmap, 2: bpp 1..3 -- one test in the store instead of two
     unsigned magic23;         // 0x4B000000 (2^23 as float bits); passed as data so that byte -> float PRMTs keep it in a register
     mm_color edge_color_x, edge_color_y;
+    // (-0, -0), (1, 1) and (1.5 * 2^23, 1.5 * 2^23) as packed float pairs, passed as data: see mm_fma2 in mm_runtime.cuh
+    unsigned long long pk_neg_zero, pk_one, pk_magic_round;
+    int vec_store;            // quad kernels: `out` and `out_stride` are multiples of 16 bytes, four RGBA8 pixels go out as one 128-bit store
     mm_image images[MM_MAX_IMAGES];
 };
 

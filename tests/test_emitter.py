@@ -13,16 +13,35 @@ def source_of(rel=None, text=None):
 
 def test_direct_output_only_when_the_pixel_is_the_sample():
     # every distortion filter ends in in(...): the sampler may hand its bytes to the store (mm_orig_val_out)
-    for rel in ("Distorts/Twirl.mm", "Distorts/Sea.mm", "Utilities/Ident.mm", "Geometry/Zoom.mm"):
+    src = source_of("Distorts/Twirl.mm")
+    assert "mm_orig_val_out(" in src and "mm_store_word(" in src
+    # ... four pixels at a time where the sample's row does not depend on the column (quad kernels)
+    for rel in ("Distorts/Sea.mm", "Utilities/Ident.mm", "Geometry/Zoom.mm"):
         src = source_of(rel)
-        assert "mm_orig_val_out(" in src and "mm_store_word(" in src, rel
+        assert "mm_orig_val_out_quad(" in src and "mm_store_quad(" in src, rel
     # a sample that is post-processed, used twice, or produced inside a conditional keeps the general path
     post = "filter f (image in)\n  c = in(xy);\n  rgba:[1-c[0], c[1], c[2], c[3]]\nend\n"
     twice = "filter g (image in)\n  c = in(xy);\n  d = c[0];\n  if d > 0.5 then c else rgba:[d, d, d, 1] end\nend\n"
     for text in (post, twice):
         src = source_of(text=text)
-        assert "mm_orig_val_out(" not in src and "mm_store_word(" not in src
+        assert "mm_orig_val_out(" not in src and "mm_orig_val_out_quad(" not in src and "mm_store_word(" not in src
     assert "mm_orig_val_out(" not in source_of("Render/Mandelbrot.mm")
+
+
+def test_quad_kernels_for_samples_whose_row_is_shared():
+    """the local-access kernel variant (four pixels of a row per thread) is chosen for straight-line pixel
+    code with a sample whose y and frame do not depend on the column; its per-pixel values are arrays of four, row-level
+    values stay scalars, a per-pixel `if` is printed once per pixel."""
+    for rel in ("Utilities/Ident.mm", "Colors/Invert.mm", "Geometry/Translate.mm", "Geometry/Scale.mm", "Distorts/Sea.mm"):
+        src = source_of(rel)
+        assert "mm_pixel_coords_quad(" in src and ("mm_orig_val_quad(" in src or "mm_orig_val_out_quad(" in src), rel
+    # a sample whose row depends on the column (rotation, twirl), per-pixel loops, or no sample at all: one pixel per thread
+    for rel in ("Distorts/Twirl.mm", "Geometry/Rotate.mm", "Render/Mandelbrot.mm", "Map/Droste.mm"):
+        assert "mm_pixel_coords_quad(" not in source_of(rel), rel
+    cond = "filter q (image in)\n  c = in(xy);\n  if c[0] > 0.5 then c else in(xy*0.5) end\nend\n"
+    src = source_of(text=cond)
+    assert "mm_pixel_coords_quad(" in src and src.count("mm_orig_val_quad(") == 1
+    assert src.count("mm_orig_val(P,") == 4  # the sample inside the per-pixel branch: once per pixel, through the one-pixel sampler
 
 
 def test_tiles_per_block_follow_the_kernel_shape():
