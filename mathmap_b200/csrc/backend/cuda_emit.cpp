@@ -781,7 +781,9 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
             fn << row_body << rv_store.str() << "}\n";
         }
         k.quad = quad;
-        fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H) " << k.kernel_name << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
+        // quad kernels wait on their texel loads: MM_QUAD_BLOCKS blocks per SM (mm_runtime.cuh)
+        fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H" << (quad ? ", MM_QUAD_BLOCKS" : "") << ") " << k.kernel_name
+           << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
            << name << " U, const __grid_constant__ mm_rowvals_" << name << " RV) {\n"
            << "    int col, mm_row0;\n"
            << (k.auto_rows > 1 ? "    const int mm_rows = P.rows;\n" : "    constexpr int mm_rows = 1;  // per-pixel loops: one tile per block\n");

@@ -816,6 +816,10 @@ MM_DEV mm_tup<4> mm_orig_val_out(const mm_params &P, int image, float x, float y
 //     share texels: 10 loads and byte -> float conversions of 40 channels instead of 16 and 64,
 //   * the four RGBA8 results leave as one 128-bit store.
 // Results are bit-identical to the one-pixel samplers: the same float operations per pixel, in the same order.
+// Quad kernels spend their time waiting for texels (up to 16 loads per strip in flight, long-scoreboard stalls lead the
+// profile), so they are compiled for more resident blocks than the compiler would choose: 4 with the bilinear sampler
+// (64 registers; 80 and 3 blocks unconstrained), 5 with the nearest one (48 registers).
+#define MM_QUAD_BLOCKS (MM_AA ? 4 : 5)
 MM_DEV void mm_pixel_coords_quad(int &col, int &row, int rows) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     col = (blockIdx.x * MM_BLOCK_W + lane) * 4;
