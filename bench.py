@@ -487,6 +487,29 @@ def measure(name, ctx, args, with_cpu):
         dt = sharding.max_over_ranks(time.perf_counter() - t0, dev)
         res["e2e"] = {"value": px_e2e * e2e_steps / dt / 1e6, "unit": "MP/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                       "steps": e2e_steps, "note": note}
+        # What the box's device->host path takes at all: every rank copies as many bytes as its share of a step's result from
+        # device memory into the same pinned host memory with plain cudaMemcpyAsync, all ranks at once.  The end-to-end rate
+        # cannot exceed this (nothing of the library runs here); at N = 8 on this pool it is the binding limit.
+        try:
+            share = d2h // world if frames == 1 else frame_bytes
+            dst = torch.from_numpy(arr.reshape(-1)[:share]) if frames == 1 else torch.from_numpy(arr.reshape(-1))
+            src = torch.empty(dst.numel(), dtype=torch.uint8, device=dev)
+            reps = 3 if frames == 1 else 3 * max(1, len(my_frames))
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            barrier()
+            dtc = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+            ceiling_bytes_s = dst.numel() * reps * world / dtc
+            res["e2e"]["d2h_ceiling"] = {"value": ceiling_bytes_s / 1e9, "unit": "GB/s", "as_metric": ceiling_bytes_s / 4 / 1e6, "metric_unit": "MP/s",
+                                         "note": "aggregate pinned cudaMemcpyAsync device->host of all ranks at once, same destination buffers"}
+            del src, dst
+        except Exception as e:  # the probe must never cost the measurement
+            res["e2e"]["d2h_ceiling"] = {"error": str(e)[:200]}
         if shared is not None:
             if rank == 0 and frames == 1:
                 # the assembled frame: rows of every rank's band are there (checked against this rank's device rows where it has them)

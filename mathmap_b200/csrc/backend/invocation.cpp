@@ -114,8 +114,14 @@ struct mmb_invocation {
     long launches = 0;
     std::string kernel_name;
     std::map<std::string, float *> coord_cache;
-    std::multimap<size_t, void *> free_blocks;              // device allocation pool
-    std::vector<std::pair<size_t, void *>> frame_blocks;    // blocks in use by the current frame
+    // Device allocation pool for per-frame temporaries.  Two lanes: frames rendered back to back on two alternating
+    // streams (mmb_render_frames_device) each recycle only what their own stream used, so stream order alone makes the
+    // reuse safe.  Everything else runs in lane 0.
+    std::multimap<size_t, void *> free_blocks[2];
+    std::vector<std::pair<size_t, void *>> frame_blocks[2];  // blocks in use by the lane's current frame
+    int lane = 0;
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_event[3] = {nullptr, nullptr, nullptr};
     std::map<std::string, int> native_cache;                // per frame: key -> image index
     void *staging = nullptr;
     size_t staging_bytes = 0;
@@ -138,22 +144,23 @@ struct mmb_invocation {
 
     void *alloc(size_t bytes) {
         bytes = (bytes + 255) & ~(size_t)255;
-        auto it = free_blocks.lower_bound(bytes);
-        if (it != free_blocks.end() && it->first <= bytes + bytes / 4) {
+        auto &fb = free_blocks[lane];
+        auto it = fb.lower_bound(bytes);
+        if (it != fb.end() && it->first <= bytes + bytes / 4) {
             void *p = it->second;
             size_t sz = it->first;
-            free_blocks.erase(it);
-            frame_blocks.push_back({sz, p});
+            fb.erase(it);
+            frame_blocks[lane].push_back({sz, p});
             return p;
         }
         void *p = nullptr;
         ck(cudaMalloc(&p, bytes), "cudaMalloc");
-        frame_blocks.push_back({bytes, p});
+        frame_blocks[lane].push_back({bytes, p});
         return p;
     }
     void release_frame_blocks() {
-        for (auto &b : frame_blocks) free_blocks.insert(b);
-        frame_blocks.clear();
+        for (auto &b : frame_blocks[lane]) free_blocks[lane].insert(b);
+        frame_blocks[lane].clear();
     }
     void *ensure_staging(void *&buf, size_t &cap, size_t bytes) {
         if (cap < bytes) {
@@ -495,8 +502,9 @@ mm_image device_desc(mmb_invocation *inv, FrameData &fd, int image, float t, int
     std::vector<unsigned char> blob;
     pack_uniform_bytes(inv, fk, crp, blob, fd, false, depth + 1);
     void *d = inv->alloc(std::max<size_t>(blob.size(), 8));
+    // pageable source: the call returns once the bytes are staged for the DMA, so the local blob may go out of scope --
+    // no stream synchronisation per closure and frame
     ck(cudaMemcpyAsync(d, blob.data(), blob.size(), cudaMemcpyHostToDevice, inv->stream), "cudaMemcpyAsync(closure uniforms)");
-    ck(cudaStreamSynchronize(inv->stream), "sync(closure uniforms)");  // blob is a local
     mm_image desc;
     memset(&desc, 0, sizeof desc);
     desc.kind = MM_IMAGE_CLOSURE;
@@ -695,8 +703,7 @@ int Replay::render_image(int idx, int width, int height, bool force) {
             for (int x = 0; x < width; ++x) c[x] = (((float)x - out.bx) / out.ax) * src.xf;
             for (int y = 0; y < height; ++y) c[(size_t)width + y] = (((float)y - out.by) / out.ay) * src.yf;
             float *d = (float *)inv->alloc(sizeof(float) * c.size());
-            ck(cudaMemcpyAsync(d, c.data(), sizeof(float) * c.size(), cudaMemcpyHostToDevice, inv->stream), "cudaMemcpyAsync(coords)");
-            ck(cudaStreamSynchronize(inv->stream), "sync(coords)");
+            ck(cudaMemcpyAsync(d, c.data(), sizeof(float) * c.size(), cudaMemcpyHostToDevice, inv->stream), "cudaMemcpyAsync(coords)");  // pageable: staged on return
             g.xs_dev = d;
             g.ys_dev = d + width;
         }
@@ -1047,8 +1054,14 @@ void mmb_invocation_free(mmb_invocation *inv) {
     cudaSetDevice(inv->device);
     if (inv->user_event_pending) cudaEventSynchronize(inv->user_event);
     cudaStreamSynchronize(inv->stream);
-    inv->release_frame_blocks();
-    for (auto &b : inv->free_blocks) cudaFree(b.second);
+    for (int l = 0; l < 2; ++l) {
+        if (inv->lane_stream[l]) { cudaStreamSynchronize(inv->lane_stream[l]); cudaStreamDestroy(inv->lane_stream[l]); }
+        inv->lane = l;
+        inv->release_frame_blocks();
+        for (auto &b : inv->free_blocks[l]) cudaFree(b.second);
+    }
+    for (auto e : inv->lane_event)
+        if (e) cudaEventDestroy(e);
     for (auto &img : inv->images)
         if (img.owned && img.data) cudaFree(img.data);
     for (auto &u : inv->uservals)
@@ -1448,11 +1461,49 @@ int mmb_calc_lines_slice_device(mmb_invocation *inv, const mmb_slice *slice, int
 int mmb_render_frames_device(mmb_invocation *inv, int n, const int *frames, const float *ts, void *device_q, void *stream) {
     if (!inv || !device_q || n < 0 || (n > 0 && !ts)) { set_error("mmb_render_frames_device: bad arguments"); return -1; }
     size_t frame_bytes = (size_t)inv->render_w * inv->render_h * inv->bpp;
-    for (int i = 0; i < n; ++i) {
-        if (mmb_init_frame(inv, frames ? frames[i] : i, ts[i]) != 0) return -1;
-        if (mmb_calc_lines_device(inv, 0, inv->render_h, (char *)device_q + frame_bytes * i, 0, stream) != 0) return -1;
+    if (n < 4) {
+        for (int i = 0; i < n; ++i) {
+            if (mmb_init_frame(inv, frames ? frames[i] : i, ts[i]) != 0) return -1;
+            if (mmb_calc_lines_device(inv, 0, inv->render_h, (char *)device_q + frame_bytes * i, 0, stream) != 0) return -1;
+        }
+        return 0;
     }
-    return 0;
+    // Consecutive frames go to two alternating streams ("lanes"), each with its own pool of per-frame temporaries, so that
+    // the ramp-up of one frame's kernels overlaps the tail of the previous frame's (a 3840x2160 frame is a 40 us kernel:
+    // back to back on one stream the SMs idle at both ends of each).  The lanes start after what the caller's (or the
+    // library's) stream has queued so far, and that stream waits for both lanes at the end.
+    int rc = guarded([&] {
+        set_device(inv);
+        for (int l = 0; l < 2; ++l)
+            if (!inv->lane_stream[l]) ck(cudaStreamCreateWithFlags(&inv->lane_stream[l], cudaStreamNonBlocking), "cudaStreamCreate");
+        for (auto &e : inv->lane_event)
+            if (!e) ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+        cudaStream_t base = stream ? (cudaStream_t)stream : inv->stream;
+        wait_for_user_stream(inv);
+        ck(cudaEventRecord(inv->lane_event[2], base), "cudaEventRecord");
+        for (int l = 0; l < 2; ++l) ck(cudaStreamWaitEvent(inv->lane_stream[l], inv->lane_event[2], 0), "cudaStreamWaitEvent");
+    });
+    if (rc != 0) return rc;
+    cudaStream_t saved = inv->stream;
+    cudaStream_t base = stream ? (cudaStream_t)stream : saved;
+    for (int i = 0; i < n && rc == 0; ++i) {
+        inv->lane = i & 1;
+        inv->stream = inv->lane_stream[inv->lane];
+        rc = mmb_init_frame(inv, frames ? frames[i] : i, ts[i]);
+        if (rc == 0) rc = mmb_calc_lines_device(inv, 0, inv->render_h, (char *)device_q + frame_bytes * i, 0, nullptr);
+    }
+    inv->lane = 0;
+    inv->stream = saved;
+    for (int l = 0; l < 2; ++l) {
+        if (cudaEventRecord(inv->lane_event[l], inv->lane_stream[l]) != cudaSuccess || cudaStreamWaitEvent(base, inv->lane_event[l], 0) != cudaSuccess) {
+            if (rc == 0) set_error("mmb_render_frames_device: stream ordering failed");
+            rc = -1;
+        }
+    }
+    // the frame state left behind belongs to lane 1's stream; the next init_frame on the library's stream must come after it
+    if (base != saved && cudaStreamWaitEvent(saved, inv->lane_event[1], 0) != cudaSuccess) rc = -1;
+    if (cudaStreamWaitEvent(saved, inv->lane_event[0], 0) != cudaSuccess) rc = -1;
+    return rc;
 }
 
 int mmb_synchronize(mmb_invocation *inv) {

@@ -504,3 +504,30 @@ def test_specialised_kernel_equals_generic(path, sets):
     want = OracleFilter(m.ir).render(W, H, dict({"in": img}, **sets), t=0.3, antialiasing=True)
     exact, le1, mx = compare_u8(outs[0], want)
     assert le1 >= 99.9, (exact, le1, mx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path,sets", [("examples/Distorts/Sea.mm", {}), ("examples/Blur/Gaussian Blur.mm", {"dev": 0.02})])
+def test_batched_frames_on_two_streams_equal_single_frames(path, sets):
+    """mmb_render_frames_device renders four or more frames on two alternating streams with separate temporaries (row
+    arrays, blur intermediates): every frame must equal the frame rendered on its own, run after run."""
+    import torch
+    W, H, n = 640, 360, 7
+    img = synthetic_rgba(W, H)
+    m = mb.Module(source=filter_source(path))
+    inv = mb.Invocation(m, W, H, antialiasing=True)
+    inv.set("in", img)
+    for k, v in sets.items():
+        inv.set(k, v)
+    ts = [f / n for f in range(n)]
+    single = [inv.render(f, ts[f]).copy() for f in range(n)]
+    out = torch.zeros((n, H, W, 4), dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        out.zero_()
+        inv.render_frames_device(out.data_ptr(), ts, list(range(n)))
+        inv.synchronize()
+        got = out.cpu().numpy()
+        for f in range(n):
+            assert np.array_equal(got[f], single[f]), f
+    # and single frames still work afterwards (lane 0, the library's own stream)
+    assert np.array_equal(inv.render(3, ts[3]), single[3])
