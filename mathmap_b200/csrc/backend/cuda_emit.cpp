@@ -2,6 +2,7 @@
 #include "../runtime/mm_types.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <set>
@@ -100,6 +101,27 @@ struct Emitter {
     // top level, where a statement is printed once (row-level values, quad samplers) or four times.
     bool quad = false;
     int qp = -1;
+    // Column statements: top-level assignments whose value depends on the column only (the reference's "y-const" values,
+    // computed once per slice by init_slice, new_template.c.in:339-373).  The pixel kernel prints them once per thread,
+    // before its loop over the block's tiles (col_phase 1), and leaves them out of the loop body (col_phase 2).
+    std::set<const Stmt *> col_stmts;
+    int col_phase = 0;
+    void find_column_statements(const Stmt *first) {
+        std::set<const Value *> col_values;
+        for (const Stmt *s = first; s; s = s->next) {
+            if (s->kind != ST_ASSIGN || s->lhs->level < 3 || !(s->lhs->const_bits & CONST_Y) || s == direct_sample || s == direct_output) continue;
+            const Rhs *r = s->rhs;
+            bool ok = r->kind == RHS_PRIMARY || r->kind == RHS_TUPLE || (r->kind == RHS_INTERNAL && r->internal == "x") ||
+                      (r->kind == RHS_OP && r->op->pure && r->op->id != OP_ORIG_VAL && r->op->id != OP_RAND && r->op->id != OP_OUTPUT_TUPLE);
+            auto arg_ok = [&](const Primary &p) { return p.is_const || p.value->index < 0 || p.value->level == 0 || col_values.count(p.value) != 0; };
+            if (ok && r->kind == RHS_PRIMARY) ok = arg_ok(r->prim);
+            if (ok && (r->kind == RHS_OP || r->kind == RHS_TUPLE))
+                for (auto &a : r->args) ok = ok && arg_ok(a);
+            if (!ok) continue;
+            col_stmts.insert(s);
+            col_values.insert(s->lhs);
+        }
+    }
     std::vector<const Value *> *spec_conds = nullptr;  // the pixel kernel only: frame-constant branch conditions (FilterKernel::spec_conds)
     std::string cond_prefix;                           // "MM_COND_<filter>_"
 
@@ -457,7 +479,8 @@ struct Emitter {
             for (const Stmt *q = s->next; q; q = q->next)
                 if (q->kind == ST_ASSIGN && q->rhs->kind == RHS_OP && q->rhs->op->id == other && on_device(q->lhs->level) &&
                     q->lhs->cv->type == T_FLOAT && !q->rhs->args[0].is_const && !s->rhs->args[0].is_const &&
-                    q->rhs->args[0].value == s->rhs->args[0].value && is_vec(q->lhs) == is_vec(s->lhs)) { mate = q; break; }
+                    q->rhs->args[0].value == s->rhs->args[0].value && is_vec(q->lhs) == is_vec(s->lhs) &&
+                    (col_stmts.count(q) != 0) == (col_stmts.count(s) != 0)) { mate = q; break; }
             if (mate) {
                 fused.insert(mate);
                 const Stmt *sn = s->rhs->op->id == OP_SIN ? s : mate, *cs = s->rhs->op->id == OP_SIN ? mate : s;
@@ -473,6 +496,7 @@ struct Emitter {
             switch (s->kind) {
             case ST_ASSIGN:
                 if (!on_device(s->lhs->level) || fused.count(s)) break;
+                if ((col_phase == 1) != (col_stmts.count(s) != 0) && col_phase != 0) break;
                 if (quad_sample(s)) {
                     const Rhs *r = s->rhs;
                     out << ind << "{ const float mm_qx[4] = " << quad_xs(r->args[0]) << "; ";
@@ -491,6 +515,7 @@ struct Emitter {
                     emit_assign(s, ind);
                 break;
             case ST_IF:
+                if (col_phase == 1) break;
                 if (!(has_device(s->cons) || has_device(s->alt) || has_device(s->exit))) break;
                 if (mode == ROW && s->level > 1) {  // per-pixel condition: only speculated pure row-level definitions live here
                     emit_stmts(s->cons, ind);
@@ -504,6 +529,7 @@ struct Emitter {
                     emit_if(s, ind);
                 break;
             case ST_WHILE:
+                if (col_phase == 1) break;
                 if (!on_device(s->level)) {
                     // a loop of another level: at most speculated definitions of this level inside
                     if (mode == ROW && s->level > 1) emit_stmts(s->body, ind);
@@ -647,6 +673,12 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         std::vector<const Value *> decls;
         e.collect_decls(code->first, decls);
         e.find_direct_output(code->first);
+        e.find_column_statements(code->first);
+        e.col_phase = 1;
+        e.emit_stmts(code->first, "    ");
+        const std::string col_body = e.out.str();
+        e.out.str("");
+        e.col_phase = 2;
         e.emit_stmts(code->first, "    ");
         std::string body = e.out.str();
         Emitter er(m, *code, Emitter::ROW, called);
@@ -781,8 +813,10 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
             fn << row_body << rv_store.str() << "}\n";
         }
         k.quad = quad;
-        // quad kernels wait on their texel loads: MM_QUAD_BLOCKS blocks per SM (mm_runtime.cuh)
-        fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H" << (quad ? ", MM_QUAD_BLOCKS" : "") << ") " << k.kernel_name
+        // quad kernels wait on their texel loads: MM_QUAD_BLOCKS blocks per SM (mm_runtime.cuh) -- unless the module calls filters or
+        // closures on the device: a register cap makes their frames spill, and the recursion through mm_closure_dispatch then
+        // overruns the device stack (IFS Functional)
+        fn << "extern \"C\" __global__ void __launch_bounds__(MM_BLOCK_W * MM_BLOCK_H" << (quad && closure_targets.empty() && called.empty() ? ", MM_QUAD_BLOCKS" : "") << ") " << k.kernel_name
            << "(const __grid_constant__ mm_params P, const __grid_constant__ mm_uniforms_"
            << name << " U, const __grid_constant__ mm_rowvals_" << name << " RV) {\n"
            << "    int col, mm_row0;\n"
@@ -800,6 +834,9 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
                << "    if (col >= P.region_w) return;\n"
                << "    const float x = __ldg(P.xs + (col + P.region_x));\n"
                << "    const float t = P.t; const int frame = P.frame; (void)t; (void)frame; (void)x;\n";
+        // every value of the pixel code is declared here, once; what depends on the column only is computed here too
+        for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << (e.is_vec(v) ? "[4]" : "") << ";\n";
+        if (!col_body.empty()) fn << "    // per column, once for all tiles of the block (init_slice, new_template.c.in:339-373)\n" << col_body;
         fn << "    // tile k of this block: compact row mm_row0 + 8 k, absolute row mm_arow0 + k * mm_astep (8-row blocks may be interleaved over\n"
            << "    // ranks), output row pointer advancing by 8 rows -- all loop-invariant work is done here, once\n"
            << "    const int mm_arow0 = mm_actual_row(P, mm_row0), mm_astep = MM_BLOCK_H * (P.row_interleave > 1 ? P.row_interleave : 1);\n"
@@ -824,7 +861,6 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
         if (have_rows) fn << rv_load.str();
         if (quad) fn << "    unsigned mm_word[4] = {0, 0, 0, 0}, mm_have = 0; (void)mm_word;\n";
         else if (e.direct_sample) fn << "    unsigned mm_word = 0; bool mm_have_word = false;\n";
-        for (const Value *v : decls) fn << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << (e.is_vec(v) ? "[4]" : "") << ";\n";
         fn << body;
         if (quad) fn << "    mm_store_quad(P, mm_outp, col, mm_np, mm_ret, mm_word, mm_have);\n";
         else
