@@ -4,15 +4,15 @@
 set -u
 OUT=${1:-gpurun_out/final}
 mkdir -p "$OUT"
-for w in mandelbrot twirl droste gauss sea ident invert; do
+for w in mandelbrot twirl droste droste_nt gauss sea ident invert perlin; do
     python bench.py --workload $w --steps 10 --warmup 3 > "$OUT/bench_$w.log" 2>&1
     tail -1 "$OUT/bench_$w.log" > "$OUT/bench_$w.json"
 done
-for w in mandelbrot twirl droste gauss sea; do
+for w in mandelbrot twirl droste gauss sea perlin; do
     ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${w}_launches.csv" \
         python bench.py --workload $w --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/ncu_launches_$w.log" 2>&1
 done
-for w in mandelbrot twirl droste sea ident; do
+for w in mandelbrot twirl droste sea ident invert perlin; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:mm_kernel -c 1 -s 3 -o "$OUT/prof_$w" -f \
         python bench.py --workload $w --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > "$OUT/ncu_full_$w.log" 2>&1
 done
