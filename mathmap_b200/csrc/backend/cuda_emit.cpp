@@ -813,6 +813,18 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
             fn << row_body << rv_store.str() << "}\n";
         }
         k.quad = quad;
+        if (e.direct_sample) {
+            // img(xy) with x, y the pixel's own coordinates and a frame-constant image and frame (pass-through, invocation.cpp)
+            const Rhs *r = e.direct_sample->rhs;
+            auto internal_is = [](const Primary &p, const char *iname) {
+                return !p.is_const && p.value->index >= 0 && p.value->def && p.value->def->kind == ST_ASSIGN && p.value->def->rhs->kind == RHS_INTERNAL &&
+                       p.value->def->rhs->internal == iname;
+            };
+            const Primary &im = r->args[2], &tt = r->args[3];
+            if (internal_is(r->args[0], "x") && internal_is(r->args[1], "y") && !im.is_const && im.value->index >= 0 && im.value->level == 0 &&
+                (tt.is_const || tt.value->index < 0 || tt.value->level == 0))
+                k.passthrough_image = im.value;
+        }
         // quad kernels wait on their texel loads: MM_QUAD_BLOCKS blocks per SM (mm_runtime.cuh) -- unless the module calls filters or
         // closures on the device: a register cap makes their frames spill, and the recursion through mm_closure_dispatch then
         // overruns the device stack (IFS Functional)

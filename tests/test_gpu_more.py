@@ -531,3 +531,34 @@ def test_batched_frames_on_two_streams_equal_single_frames(path, sets):
             assert np.array_equal(got[f], single[f]), f
     # and single frames still work afterwards (lane 0, the library's own stream)
     assert np.array_equal(inv.render(3, ts[3]), single[3])
+
+
+@pytest.mark.gpu
+def test_blur_pass_through_is_taken_and_exact():
+    """Blur/Gaussian Blur's pixel is `blurred(xy)`: the blur's horizontal pass writes the frame's rows itself (two launches per
+    frame: columns, rows) instead of a floatmap that the pixel kernel copies (three).  Same bytes either way; a region that
+    is not whole rows falls back to the pixel kernel on the finished floatmap."""
+    W, H = 512, 384
+    img = synthetic_rgba(W, H)
+    m = mb.Module(source=filter_source("examples/Blur/Gaussian Blur.mm"))
+    inv = mb.Invocation(m, W, H, antialiasing=True)
+    inv.set("in", img)
+    inv.set("dev", 0.02)
+    n0 = inv.launch_count
+    got = inv.render(0, 0.0)
+    assert inv.launch_count - n0 == 2 and inv.kernel_name == "gauss_iir_rows", (inv.launch_count - n0, inv.kernel_name)
+    want = OracleFilter(m.ir).render(W, H, {"in": img, "dev": 0.02}, antialiasing=True)
+    assert np.array_equal(got, want), compare_u8(got, want)
+    # float output takes the same path; a tile region goes through the pixel kernel and must agree with the frame
+    fm = inv.render(0, 0.0, floatmap=True)
+    assert np.array_equal(quantise_like_store(fm), got)
+    inv.init_frame(0, 0.0)
+    buf = np.zeros((40, 64, 4), np.uint8)
+    inv.calc_lines_slice(100, 140, buf, region=(32, 100, 64, 40), frame_size=(W, H))
+    assert np.array_equal(buf, got[100:140, 32:96])
+
+
+def quantise_like_store(t):
+    v = np.where(1.0 < t, np.float32(1.0), t)
+    v = np.where(0.0 < v, v, np.float32(0.0))
+    return np.floor(v.astype(np.float64) * 255.0).astype(np.uint8)
