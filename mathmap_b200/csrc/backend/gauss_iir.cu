@@ -148,36 +148,50 @@ template <class S> CK_DEV void chain_restore(Chain<S> &r, const double (&v)[4], 
 CK_DEV void cp_async4(unsigned smem_addr, const void *g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory");
 }
+CK_DEV void cp_async16(unsigned smem_addr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
 CK_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> CK_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Requests `cnt` elements of a tile: element i of the tile is the sample at lp + i * de; it lands at slot[i * CK_T + loff].
-// Floats: every thread requests its own sample (4 bytes).  Bytes: lanes 0-7 of a warp request the 4 bytes of 4
-// consecutive recursions each (cp.async moves at least 4 bytes), the other lanes request nothing.
-// One running global pointer and one shared address with immediate offsets: two integer instructions per request.
-template <class S> CK_DEV void tile_issue(S *slot, const S *lp0, long long de, int cnt, bool lvalid, int loff) {
-    if (lvalid) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(slot + loff);
-        const char *lp = (const char *)lp0;
-        de *= (long long)sizeof(S);  // byte stride: the pointer then advances by one 64-bit add per request
-        if (cnt == CK_S) {
+// How a warp fills a sample tile (CK_S steps of its 32 recursions; element i of thread tid at slot[i * CK_T + tid]).
+// The 32 recursions of a warp are 8 pixels x 4 channels, and a pixel's four channels are adjacent in memory in both
+// passes, so the lanes copy 16-byte chunks for one another:
+//   floats      a chunk = one pixel of one step (4 lanes' samples); lane l copies the pixel (l % 8) of steps l / 8 + 4m,
+//               m = 0..3: 4 requests per lane and tile instead of 16 four-byte ones, which with their 64-bit address
+//               arithmetic were a quarter of the kernel's instructions;
+//   bytes       (column pass, rows of 32 bytes per step) a chunk = 16 recursions of one step; lane l copies half (l % 2) of
+//               step l / 2: 1 request per lane and tile.  Needs rows that are multiples of 16 bytes; otherwise lanes 0-7
+//               copy the 4 bytes of one pixel each, step by step (`bytes4`).
+// The loader of a thread: which chunk column it copies (pointer of that column at the sweep's first / last sample) and where
+// it lands.
+template <class S> struct TileLoader {
+    const char *p0, *q0;  // the chunk column at own step 0 / at the other sweep's step 0
+    unsigned off;         // byte offset of the chunk column inside a tile row
+    int i_first;          // first step this lane copies
+    bool bytes4;          // bytes only: the 4-byte fallback (lanes 0-7)
+};
+template <class S> CK_DEV void tile_issue(S *slot, const TileLoader<S> &L, const char *col, long long deb, int cnt) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(slot) + L.off;
+    constexpr unsigned row = CK_T * (unsigned)sizeof(S);
+    if (sizeof(S) == 4) {
+        const char *p = col + L.i_first * deb;
 #pragma unroll
-            for (int i = 0; i < CK_S; ++i) {
-                cp_async4(sa + i * CK_T * (unsigned)sizeof(S), lp);
-                lp += de;
-            }
-        } else {
-#pragma unroll 1
-            for (int i = 0; i < cnt; ++i) {
-                cp_async4(sa + i * CK_T * (unsigned)sizeof(S), lp);
-                lp += de;
-            }
+        for (int m = 0; m < 4; ++m) {
+            if (L.i_first + 4 * m < cnt) cp_async16(sa + (L.i_first + 4 * m) * row, p);
+            p += 4 * deb;
+        }
+    } else if (!L.bytes4) {
+        if (L.i_first < cnt) cp_async16(sa + L.i_first * row, col + L.i_first * deb);
+    } else if (L.i_first == 0) {  // lanes 0-7
+        const char *p = col;
+#pragma unroll 4
+        for (int i = 0; i < cnt; ++i) {
+            cp_async4(sa + i * row, p);
+            p += deb;
         }
     }
     cp_async_commit();
-}
-template <class S> CK_DEV void warp_sync_if_shared() {
-    if (sizeof(S) == 1) __syncwarp();  // the byte ring is filled by other lanes of the warp
 }
 
 // Shared memory of a block, as separate arrays so that the compiler knows that a store of a re-run value can never
@@ -285,13 +299,15 @@ CK_DEV void own_round(const Coeffs &C, Chain<S> &st, const S *tile, const double
 // input's; OUT_RGBA8: out is bytes, line l at out + l * out_line_stride (bytes), sample k at its word k.
 template <bool ANTI, int OUT, class S>
 CK_DEV void ck_thread(const Coeffs &C, const S *in, void *out, long long out_line_stride, double *ckpt, int J, int pair, int npairs, int n,
-                      long long line_stride, long long elem_stride, const CkShared<S> &sm) {
+                      long long line_stride, long long elem_stride, bool bytes16, const CkShared<S> &sm) {
     const int tid = threadIdx.x, lane = tid & 31;
     // Threads beyond the last recursion (the last block of a picture whose line count is not a multiple of 8) run one
     // of the last line's again, in the same warp and in lockstep with the thread that owns it: they read what it reads and
     // store what it stores.  That keeps the loops free of predicates -- with the stores under a condition the compiler
     // sank the loads of the other sweep's values into the branch, right in front of their use.
-    if (pair >= npairs) pair = npairs - 4 + (pair & 3);  // the same channel of the last line
+    // (the same channel of the last line -- or, where the warp copies bytes in 16-byte chunks, the recursion 16 before it: what the
+    // repeated chunk puts into this thread's slot of the ring)
+    if (pair >= npairs) pair = (sizeof(S) == 1 && bytes16) ? pair - 16 : npairs - 4 + (pair & 3);
     const int line = pair >> 2, ch = pair & 3;
     const int h = n - n / 2;
     const int len1 = ANTI ? n - h : h, len2 = n - len1;  // own / other phase-1 lengths
@@ -302,24 +318,35 @@ CK_DEV void ck_thread(const Coeffs &C, const S *in, void *out, long long out_lin
     const S *P0 = base_in + first;   // own step 0
     const S *Q0 = base_in + last;    // the other sweep's step 0
     const double *lut = sm.lut;
-    // what this thread requests into the ring (see tile_issue)
-    const S *LP0, *LQ0;
-    bool lvalid;
-    int loff;
-    if (sizeof(S) == 1) {
-        int gpair = (blockIdx.x * CK_PAIRS) + 4 * lane;  // first of the 4 recursions lane < 8 loads for (line_stride == 4: bytes of consecutive pairs are consecutive)
-        if (gpair >= npairs) gpair = npairs - 4;     // what the clamped threads above read
-        lvalid = lane < 8;
-        const S *gb = in + (size_t)gpair;
-        LP0 = gb + first;
-        LQ0 = gb + last;
-        loff = tid - lane + 4 * lane;
-    } else {
-        lvalid = true;
-        LP0 = P0;
-        LQ0 = Q0;
-        loff = tid;
+    // what this thread copies into the ring for its warp (see TileLoader); out-of-range chunks repeat the last pixel's
+    TileLoader<S> L;
+    {
+        const int wpair0 = blockIdx.x * CK_PAIRS;  // the warp's first recursion (both warps of a block serve the same 32)
+        int gpair;
+        if (sizeof(S) == 4) {
+            gpair = wpair0 + 4 * (lane & 7);
+            if (gpair >= npairs) gpair = npairs - 4;
+            L.off = (unsigned)((tid - lane + 4 * (lane & 7)) * sizeof(S));
+            L.i_first = lane >> 3;
+            L.bytes4 = false;
+        } else if (bytes16) {
+            gpair = wpair0 + 16 * (lane & 1);
+            if (gpair >= npairs) gpair = npairs - 16;
+            L.off = (unsigned)(tid - lane + 16 * (lane & 1));
+            L.i_first = lane >> 1;
+            L.bytes4 = false;
+        } else {
+            gpair = wpair0 + 4 * (lane & 7);
+            if (gpair >= npairs) gpair = npairs - 4;
+            L.off = (unsigned)(tid - lane + 4 * (lane & 7));
+            L.i_first = lane < 8 ? 0 : 1;  // lanes 8-31 copy nothing
+            L.bytes4 = true;
+        }
+        const S *gb = in + (size_t)(gpair >> 2) * line_stride + (gpair & 3);
+        L.p0 = (const char *)(gb + first);
+        L.q0 = (const char *)(gb + last);
     }
+    const long long deb = de * (long long)sizeof(S);  // byte stride of a step
     double *ck_own = ckpt + (size_t)(ANTI ? 1 : 0) * J * 4 * npairs + pair;
     const double *ck_other = ckpt + (size_t)(ANTI ? 0 : 1) * J * 4 * npairs + pair;
 
@@ -332,18 +359,18 @@ CK_DEV void ck_thread(const Coeffs &C, const S *in, void *out, long long out_lin
 #pragma unroll
     for (int j = 0; j < CK_R - 1; ++j) {
         const int c = len1 - j * CK_S;
-        tile_issue(&sm.ring[j % CK_R][0][0], LP0 + (long long)j * CK_S * de, de, c < CK_S ? (c < 0 ? 0 : c) : CK_S, lvalid, loff);
+        tile_issue(&sm.ring[j % CK_R][0][0], L, L.p0 + (long long)j * CK_S * deb, deb, c < CK_S ? (c < 0 ? 0 : c) : CK_S);
     }
     int slot = 0;  // j % CK_R
 #pragma unroll 1
     for (int j = 0; j < J1; ++j) {
-        warp_sync_if_shared<S>();  // the slot refilled below was read by other lanes in the previous round
+        __syncwarp();  // the slot refilled below was read by other lanes in the previous round
         {
             const int jn = j + CK_R - 1, c = len1 - jn * CK_S;
-            tile_issue(&sm.ring[slot == 0 ? CK_R - 1 : slot - 1][0][0], LP0 + (long long)jn * CK_S * de, de, c < CK_S ? (c < 0 ? 0 : c) : CK_S, lvalid, loff);
+            tile_issue(&sm.ring[slot == 0 ? CK_R - 1 : slot - 1][0][0], L, L.p0 + (long long)jn * CK_S * deb, deb, c < CK_S ? (c < 0 ? 0 : c) : CK_S);
         }
         cp_async_wait<CK_R - 1>();
-        warp_sync_if_shared<S>();
+        __syncwarp();
         const S *tile = &sm.ring[slot][0][tid];
         const int cnt = len1 - j * CK_S < CK_S ? len1 - j * CK_S : CK_S;
         if (j == 0) {
@@ -395,7 +422,7 @@ CK_DEV void ck_thread(const Coeffs &C, const S *in, void *out, long long out_lin
     for (int k = 0; k < CK_R - 1; ++k) {
         const int jb = J2 - 1 - k;
         const int c = jb >= 0 ? (len2 - jb * CK_S < CK_S ? len2 - jb * CK_S : CK_S) : 0;
-        tile_issue(&sm.ring[slot_below(oslot, k)][0][0], LQ0 - (long long)jb * CK_S * de, -de, c, lvalid && jb >= 0, loff);
+        tile_issue(&sm.ring[slot_below(oslot, k)][0][0], L, L.q0 - (long long)jb * CK_S * deb, -deb, c);
     }
     double ckv[4] = {0, 0, 0, 0};
     S hs[4] = {S(0), S(0), S(0), S(0)};
@@ -407,7 +434,7 @@ CK_DEV void ck_thread(const Coeffs &C, const S *in, void *out, long long out_lin
             chain_restore(r, ckv, hs, lut);
         }
         cp_async_wait<CK_R - 2>();
-        warp_sync_if_shared<S>();
+        __syncwarp();
         rerun_block(r, &sm.ring[oslot][0][tid], J2 - 1, len2 - (J2 - 1) * CK_S);
         if (J2 - 2 >= 1) load_checkpoint(J2 - 2, ckv, hs);
     }
@@ -415,16 +442,16 @@ CK_DEV void ck_thread(const Coeffs &C, const S *in, void *out, long long out_lin
     for (int jb = J2 - 1; jb >= 0; --jb) {
         const int cnt = len2 - jb * CK_S < CK_S ? len2 - jb * CK_S : CK_S;
         const int t0 = n - (jb * CK_S + cnt);  // own steps t0 .. t0+cnt-1 cover the other sweep's block jb
-        warp_sync_if_shared<S>();
+        __syncwarp();
         {
             const int jn = jb - (CK_R - 1);
-            tile_issue(&sm.ring[slot_below(oslot, CK_R - 1)][0][0], LQ0 - (long long)jn * CK_S * de, -de, CK_S, lvalid && jn >= 0, loff);
+            tile_issue(&sm.ring[slot_below(oslot, CK_R - 1)][0][0], L, L.q0 - (long long)jn * CK_S * deb, -deb, jn >= 0 ? CK_S : 0);
         }
         double nckv[4] = {0, 0, 0, 0};
         S nhs[4] = {S(0), S(0), S(0), S(0)};
         if (jb - 2 >= 1) load_checkpoint(jb - 2, nckv, nhs);  // used in the next round
         cp_async_wait<CK_R - 2>();  // all but the latest CK_R - 2 tiles have landed: tiles jb and jb - 1
-        warp_sync_if_shared<S>();
+        __syncwarp();
         const S *otile = &sm.ring[oslot][0][tid];
         const S *rtile = &sm.ring[slot_below(oslot, 1)][0][tid];
         OutCursor<OUT> oc;
@@ -459,7 +486,7 @@ CK_DEV void ck_thread(const Coeffs &C, const S *in, void *out, long long out_lin
 
 template <class S, int OUT>
 __global__ void __launch_bounds__(CK_T, 7) gauss_iir_ckpt_kernel(const S *in, void *out, long long out_line_stride, double *ckpt, int nlines, int n,
-                                                                  long long line_stride, long long elem_stride, int J, const __grid_constant__ Coeffs C) {
+                                                                  long long line_stride, long long elem_stride, int J, int bytes16, const __grid_constant__ Coeffs C) {
     __shared__ double sh_w[CK_S][CK_T];
     __shared__ S sh_ring[CK_R][CK_S][CK_T];
     __shared__ double sh_lut[sizeof(S) == 1 ? 256 : 1];
@@ -471,8 +498,8 @@ __global__ void __launch_bounds__(CK_T, 7) gauss_iir_ckpt_kernel(const S *in, vo
     const bool anti = threadIdx.x >= CK_PAIRS;
     const int npairs = nlines * 4;
     const int pair = blockIdx.x * CK_PAIRS + (threadIdx.x - (anti ? CK_PAIRS : 0));
-    if (anti) ck_thread<true, OUT>(C, in, out, out_line_stride, ckpt, J, pair, npairs, n, line_stride, elem_stride, sm);
-    else ck_thread<false, OUT>(C, in, out, out_line_stride, ckpt, J, pair, npairs, n, line_stride, elem_stride, sm);
+    if (anti) ck_thread<true, OUT>(C, in, out, out_line_stride, ckpt, J, pair, npairs, n, line_stride, elem_stride, bytes16 != 0, sm);
+    else ck_thread<false, OUT>(C, in, out, out_line_stride, ckpt, J, pair, npairs, n, line_stride, elem_stride, bytes16 != 0, sm);
 }
 
 int ckpt_blocks(int n) { return ((n - n / 2) + CK_S - 1) / CK_S + 1; }
@@ -486,8 +513,10 @@ void launch_pass(const S *in, void *out, long long out_line_stride, double *ckpt
     gauss_iir_constants_host(sigma, raw);
     memcpy(&c, raw, sizeof c);
     const int npairs = nlines * 4;
+    // bytes: 16-byte chunks need rows of the picture that start and end on 16-byte boundaries
+    const int bytes16 = sizeof(S) == 1 && npairs % 16 == 0 && ((uintptr_t)in & 15) == 0 && (elem_stride & 15) == 0;
     gauss_iir_ckpt_kernel<S, OUT><<<(npairs + CK_PAIRS - 1) / CK_PAIRS, CK_T, 0, stream>>>(in, out, out_line_stride, ckpt, nlines, n, line_stride,
-                                                                                          elem_stride, ckpt_blocks(n), c);
+                                                                                          elem_stride, ckpt_blocks(n), bytes16, c);
 }
 
 }  // namespace

@@ -1523,6 +1523,7 @@ int mmb_gaussian_blur_device(int device, const float *device_in, float *device_o
                              void *stream) {
     return guarded([&] {
         ck(cudaSetDevice(device), "cudaSetDevice");
+        if ((((uintptr_t)device_in | (uintptr_t)device_out) & 15) != 0) fail("mmb_gaussian_blur_device: float4 pixels must be 16-byte aligned");
         cudaStream_t s = (cudaStream_t)stream;
         size_t bytes = sizeof(float) * 4 * (size_t)width * height;
         if (sigma_h_px < 0.5f || sigma_v_px < 0.5f) {

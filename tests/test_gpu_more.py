@@ -562,3 +562,22 @@ def quantise_like_store(t):
     v = np.where(1.0 < t, np.float32(1.0), t)
     v = np.where(0.0 < v, v, np.float32(0.0))
     return np.floor(v.astype(np.float64) * 255.0).astype(np.uint8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(36, 35), (44, 21), (33, 40), (20, 50), (130, 17), (8, 8)])
+def test_blur_of_a_drawable_at_ragged_sizes(w, h):
+    """The blur's column pass reads the RGBA8 drawable itself: in 16-byte chunks where the rows allow it (width a multiple
+    of 4), 4 bytes at a time otherwise; blocks that hang over the right edge repeat the last pixels.  Bytes and floats must
+    equal the oracle's."""
+    img = synthetic_rgba(w, h, seed=w * 100 + h)
+    m = mb.Module(source=filter_source("examples/Blur/Gaussian Blur.mm"))
+    inv = mb.Invocation(m, w, h, antialiasing=True)
+    inv.set("in", img)
+    inv.set("dev", 0.05)
+    got = inv.render(0, 0.0)
+    gotf = inv.render(0, 0.0, floatmap=True)
+    o = OracleFilter(m.ir)
+    assert np.array_equal(got, o.render(w, h, {"in": img, "dev": 0.05}, antialiasing=True))
+    wantf = o.render(w, h, {"in": img, "dev": 0.05}, antialiasing=True, floatmap=True)
+    assert np.array_equal(gotf.view(np.uint32), wantf.view(np.uint32))

@@ -126,7 +126,7 @@ static void timing(int w, int h, float sigma, bool bytes) {
 int main(int argc, char **argv) {
     const int big = argc > 1 ? atoi(argv[1]) : 8192;
     long bad = 0;
-    const int shapes[][2] = {{1, 1}, {2, 3}, {7, 5}, {9, 1}, {1, 9}, {33, 17}, {130, 40}, {40, 130}, {1000, 37}, {37, 1000}, {517, 1031}, {64, 64}, {257, 255}, {31, 33}, {8, 16}, {16, 8}, {35, 36}, {36, 35}, {63, 65}, {66, 67}};
+    const int shapes[][2] = {{1, 1}, {2, 3}, {7, 5}, {9, 1}, {1, 9}, {33, 17}, {130, 40}, {40, 130}, {1000, 37}, {37, 1000}, {517, 1031}, {64, 64}, {257, 255}, {31, 33}, {8, 16}, {16, 8}, {35, 36}, {36, 35}, {63, 65}, {66, 67}, {44, 21}, {20, 50}, {52, 19}, {12, 300}, {100, 9}};
     if (argc <= 2)
     for (auto &s : shapes)
         for (int mode = 0; mode < 3; ++mode) bad += check(s[0], s[1], 3.0f + (s[0] % 7), 0.7f + (s[1] % 5) * 2.5f, mode);
