@@ -911,6 +911,10 @@ MM_DEV unsigned mm_nearest_quad(const mm_params &P, const mm_image &img, const f
     }
     if (!inside) return 0u;
     const unsigned *row = img.fast_base + ((unsigned)__float_as_int(mm_floor_biased(py)) & 0x7fffffu) * (unsigned)img.w;
+    // The block's next tile is eight rows down: at unit scale its texel row is eight rows down too, requested into L2 now
+    // (a guess that costs one instruction; inside the image by the test).  Measured on Invert 8192^2: 0.145 -> 0.137 ms;
+    // the bilinear sampler, which waits on L1 / L2 hits rather than on DRAM, gained nothing from the same hint.
+    if (py + 8.0f < img.fast_h) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 8u * (unsigned)img.w + (unsigned)__float_as_int(mm_floor_biased(px[0]))));
     const unsigned magic = P.magic23;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
