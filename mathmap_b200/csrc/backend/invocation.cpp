@@ -1519,29 +1519,45 @@ int mmb_synchronize(mmb_invocation *inv) {
 long mmb_launch_count(const mmb_invocation *inv) { return inv ? inv->launches : -1; }
 const char *mmb_kernel_name(const mmb_invocation *inv) { return inv ? inv->kernel_name.c_str() : nullptr; }
 
+// Work memory of mmb_gaussian_blur_device, kept per device between calls (grow-only): no cudaMalloc / cudaFree per call.
+// Calls on one device are serialised by the mutex, and a call waits for its own work before it returns, so the buffers
+// are free again when the next call takes them.
+namespace {
+struct BlurScratch {
+    void *buf[3] = {nullptr, nullptr, nullptr};
+    size_t cap[3] = {0, 0, 0};
+    void *get(int i, size_t bytes) {
+        if (cap[i] < bytes) {
+            if (buf[i]) cudaFree(buf[i]);
+            buf[i] = nullptr;
+            cap[i] = 0;
+            ck(cudaMalloc(&buf[i], bytes), "cudaMalloc(blur work memory)");
+            cap[i] = bytes;
+        }
+        return buf[i];
+    }
+};
+std::mutex g_blur_mu;
+std::map<int, BlurScratch> g_blur_scratch;
+}  // namespace
+
 int mmb_gaussian_blur_device(int device, const float *device_in, float *device_out, int width, int height, float sigma_h_px, float sigma_v_px,
                              void *stream) {
     return guarded([&] {
         ck(cudaSetDevice(device), "cudaSetDevice");
         if ((((uintptr_t)device_in | (uintptr_t)device_out) & 15) != 0) fail("mmb_gaussian_blur_device: float4 pixels must be 16-byte aligned");
+        if (width <= 0 || height <= 0) return;
         cudaStream_t s = (cudaStream_t)stream;
         size_t bytes = sizeof(float) * 4 * (size_t)width * height;
-        if (sigma_h_px < 0.5f || sigma_v_px < 0.5f) {
-            void *tmp = nullptr, *curves = nullptr;
-            ck(cudaMalloc(&tmp, bytes), "cudaMalloc");
-            ck(cudaMalloc(&curves, gauss_rle_curve_bytes(sigma_h_px, sigma_v_px)), "cudaMalloc");
-            launch_gauss_rle(device_in, (float *)tmp, device_out, width, height, sigma_h_px, sigma_v_px, curves, s);
-            cudaStreamSynchronize(s);
-            cudaFree(tmp);
-            cudaFree(curves);
-        } else {
-            void *scratch = nullptr;
-            ck(cudaMalloc(&scratch, gauss_iir_scratch_bytes(width, height)), "cudaMalloc(scratch)");
-            launch_gauss_iir(device_in, false, device_out, (double *)scratch, width, height, sigma_h_px, sigma_v_px, s);
-            cudaStreamSynchronize(s);
-            cudaFree(scratch);
-        }
-        ck(cudaGetLastError(), "gaussian blur");
+        std::lock_guard<std::mutex> lock(g_blur_mu);
+        BlurScratch &w = g_blur_scratch[device];
+        if (sigma_h_px < 0.5f || sigma_v_px < 0.5f)
+            launch_gauss_rle(device_in, (float *)w.get(0, bytes), device_out, width, height, sigma_h_px, sigma_v_px,
+                             w.get(1, gauss_rle_curve_bytes(sigma_h_px, sigma_v_px)), s);
+        else
+            launch_gauss_iir(device_in, false, device_out, (double *)w.get(2, gauss_iir_scratch_bytes(width, height)), width, height, sigma_h_px, sigma_v_px, s);
+        ck(cudaGetLastError(), "gaussian blur launch");
+        ck(cudaStreamSynchronize(s), "gaussian blur");
     });
 }
 
