@@ -819,7 +819,9 @@ MM_DEV mm_tup<4> mm_orig_val_out(const mm_params &P, int image, float x, float y
 // Quad kernels spend their time waiting for texels (up to 16 loads per strip in flight, long-scoreboard stalls lead the
 // profile), so they are compiled for more resident blocks than the compiler would choose: 4 with the bilinear sampler
 // (64 registers; 80 and 3 blocks unconstrained), 5 with the nearest one (48 registers).
+#ifndef MM_QUAD_BLOCKS
 #define MM_QUAD_BLOCKS (MM_AA ? 4 : 5)
+#endif
 MM_DEV void mm_pixel_coords_quad(int &col, int &row, int rows) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     col = (blockIdx.x * MM_BLOCK_W + lane) * 4;
