@@ -204,20 +204,15 @@ template <class S> struct CkShared {
 };
 
 // Where a pass's results go.  OUT_FLOAT: a float image laid out like the input (its own line stride).  OUT_RGBA8 (the
-// row pass only, when the filter's pixel IS the blurred sample, see invocation.cpp): the pixel's four channels sit in
-// four adjacent lanes, each quantises its value like the pixel kernel's store (mm_runtime.cuh: mm_clamp01 with the
-// template's MIN/MAX, times 255.0 truncated, new_template.c.in:272-293), two shuffles gather the bytes and the lane of
-// channel 0 stores the word.
+// row pass only, when the filter's pixel IS the blurred sample, see invocation.cpp): every thread quantises its channel like
+// the pixel kernel's store (mm_runtime.cuh: mm_clamp01 with the template's MIN/MAX, times 255.0 truncated,
+// new_template.c.in:272-293) and stores its byte; the four channel lanes of a pixel write one word between them (the
+// LSU merges them), which measured faster than gathering the word with two shuffles per step.
 enum { OUT_FLOAT = 0, OUT_RGBA8 = 1 };
 CK_DEV unsigned quant_byte(float v) {
     const float m = (1.0f < v) ? 1.0f : v;   // MIN(1, v): NaN stays
     const float c = (0.0f < m) ? m : 0.0f;   // MAX(0, m): NaN -> 0
     return (unsigned)__float_as_int(__fmaf_rz(c, 255.0f, 8388608.0f)) & 0xffu;  // 2^23 + floor(c * 255), exact product
-}
-CK_DEV unsigned pack_pixel(float v) {
-    const unsigned q = quant_byte(v);
-    const unsigned t = q | (__shfl_xor_sync(0xffffffffu, q, 1) << 8);
-    return t | (__shfl_xor_sync(0xffffffffu, t, 2) << 16);
 }
 template <int OUT> struct OutCursor;
 template <> struct OutCursor<OUT_FLOAT> {
@@ -227,13 +222,12 @@ template <> struct OutCursor<OUT_FLOAT> {
     CK_DEV void put4(float a, float b, float c, float d) { p[0] = a; p[de] = b; p[2 * de] = c; p[3 * de] = d; p += 4 * de; }
 };
 template <> struct OutCursor<OUT_RGBA8> {
-    unsigned *p;   // the pixel of the next step in this thread's row
-    int dir;       // +1 / -1 pixel per step
-    bool writer;   // the lane of channel 0
-    CK_DEV void put(float v) { const unsigned w = pack_pixel(v); if (writer) *p = w; p += dir; }
+    unsigned char *p;  // this thread's channel byte of the pixel of the next step in its row
+    int dir;           // +4 / -4 bytes per step
+    CK_DEV void put(float v) { *p = (unsigned char)quant_byte(v); p += dir; }
     CK_DEV void put4(float a, float b, float c, float d) {
-        const unsigned wa = pack_pixel(a), wb = pack_pixel(b), wc = pack_pixel(c), wd = pack_pixel(d);
-        if (writer) { p[0] = wa; p[dir] = wb; p[2 * dir] = wc; p[3 * dir] = wd; }
+        p[0] = (unsigned char)quant_byte(a); p[dir] = (unsigned char)quant_byte(b);
+        p[2 * dir] = (unsigned char)quant_byte(c); p[3 * dir] = (unsigned char)quant_byte(d);
         p += 4 * dir;
     }
 };
@@ -459,9 +453,8 @@ CK_DEV void ck_thread(const Coeffs &C, const S *in, void *out, long long out_lin
             oc.p = (float *)out + (size_t)line * out_line_stride + ch + first + (long long)t0 * de;
             oc.de = de;
         } else {
-            oc.p = (unsigned *)((char *)out + (size_t)line * out_line_stride) + (ANTI ? n - 1 - t0 : t0);
-            oc.dir = ANTI ? -1 : 1;
-            oc.writer = ch == 0;
+            oc.p = (unsigned char *)out + (size_t)line * out_line_stride + (size_t)(ANTI ? n - 1 - t0 : t0) * 4 + ch;
+            oc.dir = ANTI ? -4 : 4;
         }
         Chain<S> r;
         chain_clear(r);
