@@ -46,7 +46,7 @@ WORKLOADS = {
     "droste_nt": dict(script="Map/Droste.mm", ir="droste.mmir", w=8192, h=8192, uv={"NoTransparency": 1}, aa=True, frames=1, input=True, bytes_px=8,
                       desc="Map/Droste.mm -i -DNoTransparency=1, synthetic 8192x8192 RGBA8 input"),
     "gauss": dict(script="Blur/Gaussian Blur.mm", ir="gauss.mmir", w=8192, h=8192, uv={"dev": 0.0078134}, aa=True, frames=1, input=True, bytes_px=40,
-                  desc="Blur/Gaussian Blur.mm -i -Ddev=0.0078134 (sigma 32 px), synthetic 8192x8192 RGBA8 input"),
+                  bands="contiguous", desc="Blur/Gaussian Blur.mm -i -Ddev=0.0078134 (sigma 32 px), synthetic 8192x8192 RGBA8 input"),
     "sea": dict(script="Distorts/Sea.mm", ir="sea.mmir", w=3840, h=2160, uv={}, aa=True, frames=240, input=True, bytes_px=4,
                 desc="Distorts/Sea.mm -i, synthetic 3840x2160 RGBA8 input, 240 frames t=f/240"),
     "ident": dict(script="Utilities/Ident.mm", ir="ident.mmir", w=8192, h=8192, uv={}, aa=True, frames=1, input=True, bytes_px=8,
@@ -223,7 +223,9 @@ def workload_config(name, world=1, fast_math=False):
     W, H, frames = wl["w"], wl["h"], wl["frames"]
     cfg = {"workload": wl["desc"], "filter": wl["script"], "width": W, "height": H, "frames_per_step": frames,
            "math": "float libm" if fast_math else "libm evaluated in double and narrowed (parity mode)",
-           "sharding": ("one frame, 8-row blocks interleaved over ranks" if frames == 1 else "frames round-robin over ranks") if world > 1 else "single GPU",
+           "sharding": (("one frame, contiguous row bands (mathmap_common.c:997-998): every rank runs the blur's vertical pass over the whole picture "
+                         "(replicated work) and its horizontal pass over its own band" if WORKLOADS[name].get("bands") == "contiguous"
+                         else "one frame, 8-row blocks interleaved over ranks") if frames == 1 else "frames round-robin over ranks") if world > 1 else "single GPU",
            "l2": "no L2 flush needed: each step writes %d MiB of output%s, larger than the 126 MB L2"
                  % (W * H * 4 * frames >> 20, " and samples a %d MiB input" % (W * H * 4 >> 20) if wl["input"] else "")}
     return cfg
@@ -333,7 +335,9 @@ def measure(name, ctx, args, with_cpu):
 
     # this rank's share of a step
     if frames == 1:
-        my_rows = len(sharding.interleaved_rows_for_rank(H, rank, world))
+        contiguous = wl.get("bands") == "contiguous"  # uniform cost per row: the reference's own band split
+        band = sharding.band_for_rank(0, H, rank, world)
+        my_rows = band[1] - band[0] if contiguous else len(sharding.interleaved_rows_for_rank(H, rank, world))
         out = torch.empty((max(1, (my_rows + 7) // 8 * 8), W, 4), dtype=torch.uint8, device=dev)
         my_frames = [0]
         pixels_per_step_all = W * H
@@ -342,6 +346,8 @@ def measure(name, ctx, args, with_cpu):
             inv.init_frame(0, 0.0)
             if world == 1:
                 inv.calc_lines_device(out.data_ptr(), 0, H)
+            elif contiguous:
+                inv.calc_lines_device(out.data_ptr(), band[0], band[1])
             else:
                 inv.calc_lines_interleaved_device(out.data_ptr(), rank, world)
     else:
