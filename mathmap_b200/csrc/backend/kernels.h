@@ -20,10 +20,6 @@ void launch_gauss_iir(const void *in, bool in_is_rgba8, float *out, double *scra
 void launch_gauss_iir_columns(const void *in, bool in_is_rgba8, float *mid, double *scratch, int width, int height, float sigma_v, cudaStream_t stream);
 void launch_gauss_iir_rows(const float *mid, void *out, bool rgba8, long long out_pitch, double *scratch, int width, int first_row, int nrows, float sigma_h,
                            cudaStream_t stream);
-// round-1 kernel (full double scratch), kept for A/B runs of tools/gauss_dev.cu
-size_t gauss_iir_scratch_bytes_r01(int width, int height);
-void launch_gauss_iir_r01(const void *in, bool in_is_rgba8, float *out, double *scratch, int width, int height, float sigma_h, float sigma_v,
-                          cudaStream_t stream);
 size_t gauss_rle_curve_bytes(float sigma_h, float sigma_v);
 void launch_gauss_rle(const float *in, float *tmp, float *out, int width, int height, float sigma_h, float sigma_v, void *curve_mem, cudaStream_t stream);
 void gauss_iir_constants_host(float std_dev, double *out30);

@@ -1,5 +1,5 @@
 // Developer harness for the Gaussian IIR passes (not part of the library or the tests): runs the shipped kernel
-// (mmbackend::launch_gauss_iir) and the round-1 full-scratch kernel (launch_gauss_iir_r01) on the same inputs, compares
+// (mmbackend::launch_gauss_iir) and the round-1 full-scratch kernel (tools/gauss_r01.cuh) on the same inputs, compares
 // raw float bits (NaN == NaN) and times both with CUDA events.
 //   tools/build_gauss_dev.sh && tools/_bin/gauss_dev [size]
 #include <cuda_runtime.h>
@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../mathmap_b200/csrc/backend/kernels.h"
+#include "gauss_r01.cuh"
 
 using namespace mmbackend;
 
