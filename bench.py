@@ -14,7 +14,7 @@ and perlin (the libnoise showcase), and carries them in the same JSON line under
 
 N > 1 is launched by torchrun, one rank per GPU.  Single-frame workloads split the frame into
 8-row blocks interleaved over the ranks (strong scaling, no data-path collective; input
-drawables are replicated by one NCCL broadcast); sea renders its 240 frames round-robin over the
+drawables: every rank uploads one band of rows, one NCCL all-gather replicates); sea renders its 240 frames round-robin over the
 ranks.  The blur of `gauss` produces a whole-image intermediate and is computed by every rank
 ("replicas only" for that stage).
 
@@ -318,18 +318,19 @@ def measure(name, ctx, args, with_cpu):
         inv.set(k, v)
     h2d_bytes = 0
     host_input = d_in = None
+    in_band = sharding.band_for_rank(0, H, rank, world)
     if wl["input"]:
-        # rank 0 makes the drawable; one NCCL broadcast replicates it (samplers read arbitrary coordinates)
+        # every rank can read the (synthetic, seeded) host image: it pins and uploads its own band of rows, and one all-gather
+        # over NVLink replicates the drawable (samplers read arbitrary coordinates); at N = 1 that is the whole image
         d_in = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
-        if rank == 0:
-            key = (W, H)
-            if key not in ctx.host_inputs:
-                ctx.host_inputs[key] = synthetic_input(W, H)
-            if key not in ctx.pinned_inputs:
-                ctx.pinned_inputs[key] = torch.from_numpy(ctx.host_inputs[key]).pin_memory()
-            host_input = ctx.pinned_inputs[key]
-            d_in.copy_(host_input)
-        sharding.broadcast_drawable(d_in, src=0)
+        key = (W, H)
+        if key not in ctx.host_inputs:
+            ctx.host_inputs[key] = synthetic_input(W, H)
+        if key not in ctx.pinned_inputs:
+            ctx.pinned_inputs[key] = torch.from_numpy(np.ascontiguousarray(ctx.host_inputs[key][in_band[0]:in_band[1]])).pin_memory()
+        host_input = ctx.pinned_inputs[key]
+        d_in[in_band[0]:in_band[1]].copy_(host_input)
+        sharding.replicate_drawable_bands(d_in)
         inv.set("in", d_in)
         h2d_bytes = W * H * 4
 
@@ -439,7 +440,7 @@ def measure(name, ctx, args, with_cpu):
                                             "makes this the binding roofline, the HBM one above is what SURVEY.md section 8d asks for" % sm_mhz}
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region:
-    # H2D of the step's input (rank 0, then one NCCL broadcast at N > 1), mmb_init_frame, mmb_calc_lines into host memory
+    # H2D of the step's input (at N > 1 one band of rows per rank, then one NCCL all-gather), mmb_init_frame, mmb_calc_lines into host memory
     if not args.no_e2e:
         e2e_steps = args.steps
         frame_bytes = W * H * 4
@@ -450,9 +451,8 @@ def measure(name, ctx, args, with_cpu):
             if world == 1:
                 inv.set("in", host_input.numpy())  # H2D of the step's input through the public API
             else:
-                if rank == 0:
-                    d_in.copy_(host_input, non_blocking=True)
-                sharding.broadcast_drawable(d_in, src=0)
+                d_in[in_band[0]:in_band[1]].copy_(host_input, non_blocking=True)
+                sharding.replicate_drawable_bands(d_in)
                 torch.cuda.current_stream().synchronize()
                 inv.set("in", d_in)
 
@@ -468,7 +468,7 @@ def measure(name, ctx, args, with_cpu):
                 inv.calc_lines(rows[0], rows[1], out=arr)
             px_e2e = W * H
             d2h = frame_bytes
-            note = ("mmb_set_userval_image_host / NCCL broadcast + mmb_init_frame + mmb_calc_lines; contiguous bands per rank, every rank "
+            note = ("mmb_set_userval_image_host (N > 1: each rank uploads its band of the input, one NCCL all-gather) + mmb_init_frame + mmb_calc_lines; contiguous bands per rank, every rank "
                     "copies its band into ONE pinned host frame shared by the ranks")
         else:
             shared = None
@@ -571,6 +571,8 @@ def main():
     except (OSError, ValueError):
         pass
     if world > 1:
+        # stdout carries the one JSON line: NCCL's own banner ("NCCL version ..." at NCCL_DEBUG=VERSION / WARN) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=ctx.dev)
 
     with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
@@ -586,12 +588,17 @@ def main():
         for name in WORKLOADS:
             if name == HEADLINE:
                 continue
+            ok = 1
             try:
                 per[name] = measure(name, ctx, args, with_cpu)
             except Exception as e:  # one workload failing must not lose the headline line; the failure is reported in its place
-                if world > 1:
-                    raise
                 per[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                ok = 0
+            if world > 1:  # the ranks agree on the outcome, so that a failure on one of them is not reported as a number by rank 0
+                flag = torch.tensor([ok], device=ctx.dev, dtype=torch.int32)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if ok and int(flag.item()) == 0:
+                    per[name] = {"error": "failed on another rank"}
         line["per_workload"] = per
 
     if rank == 0:

@@ -5,8 +5,9 @@ The path shards without any data-path exchange: pixels are independent given rea
   * one large frame split into row bands: contiguous, with the reference's own formula
     rows [y0 + h*i/n, y0 + h*(i+1)/n) (mathmap_common.c:997-998), or 8-row blocks interleaved
     across ranks when the filter's cost varies over the image (escape-time fractals)
-  * input drawables are replicated to every GPU with one broadcast (NCCL over NVLink on GPUs,
-    gloo in the CPU tests), because samplers read arbitrary coordinates.
+  * input drawables are replicated to every GPU, because samplers read arbitrary coordinates: with one
+    broadcast from the rank that holds the image, or -- when every rank can read the host image -- each rank
+    uploads one band and one all-gather replicates (NCCL over NVLink on GPUs, gloo in the CPU tests).
 torch.distributed is plumbing only.
 """
 import numpy as np
@@ -46,6 +47,26 @@ def broadcast_drawable(tensor, src=0):
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.broadcast(tensor, src=src)
+    return tensor
+
+
+def replicate_drawable_bands(tensor):
+    """Replicates an input drawable of which every rank has uploaded only its own contiguous band (band_for_rank over the
+    rows of `tensor`, uint8 [H, W, 4], allocated on every rank): the host->device traffic of the frame is spread over the
+    ranks' own PCIe links, and the bands travel between the GPUs once (one in-place all-gather over NVLink when the
+    bands are equal, else one broadcast per band)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tensor
+    world, rank, h = dist.get_world_size(), dist.get_rank(), tensor.shape[0]
+    if h % world == 0 and dist.get_backend() == "nccl" and tensor.is_contiguous():
+        r0, r1 = band_for_rank(0, h, rank, world)
+        dist.all_gather_into_tensor(tensor.view(-1), tensor[r0:r1].view(-1))  # in place: the send buffer is this rank's slot
+    else:
+        for r in range(world):
+            r0, r1 = band_for_rank(0, h, r, world)
+            if r1 > r0:
+                dist.broadcast(tensor[r0:r1], src=r)
     return tensor
 
 

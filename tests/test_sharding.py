@@ -42,6 +42,13 @@ def _worker(rank, world, port, q):
     sharding.broadcast_drawable(t, src=0)
     mx = sharding.max_over_ranks(1.0 + rank)
     frames = sharding.frames_for_rank(10, rank, world)
+    # every rank holds only its own band of a drawable (an odd number of rows: unequal bands), then all have all of it
+    whole = torch.arange(7 * 3 * 4, dtype=torch.uint8).reshape(7, 3, 4)
+    part = torch.zeros_like(whole)
+    r0, r1 = sharding.band_for_rank(0, 7, rank, world)
+    part[r0:r1] = whole[r0:r1]
+    sharding.replicate_drawable_bands(part)
+    assert torch.equal(part, whole)
     q.put((rank, int(t.sum()), mx, frames))
     dist.destroy_process_group()
 
