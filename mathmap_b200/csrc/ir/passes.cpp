@@ -653,9 +653,15 @@ void analyze_constants(FilterCode &code) {
                 int cb = rhs_bits(s->cond) & ctrl;
                 go(s->cons, cb);
                 go(s->alt, cb);
+                // A phi of an `if` is a pure function of the condition and its two inputs: the control AROUND the `if` decides
+                // whether the value is needed, not what it is.  (The reference limits it by the enclosing conditions too,
+                // compiler.c analyze_phis_constants' const_max, and then builds e.g. the closure of an inlined image
+                // argument per pixel inside a loop; here such a value is a frame constant, computed by the host replay,
+                // which already speculates pure definitions under per-pixel control.)
+                const int own = rhs_bits(s->cond);
                 for (Stmt *p = s->exit; p; p = p->next) {
                     if (p->kind != ST_PHI) continue;
-                    int b = rhs_bits(p->rhs) & rhs_bits(p->rhs2) & cb;
+                    int b = rhs_bits(p->rhs) & rhs_bits(p->rhs2) & own;
                     if ((p->lhs->const_bits & b) != p->lhs->const_bits) { p->lhs->const_bits &= b; changed = true; }
                 }
                 break;

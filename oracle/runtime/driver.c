@@ -142,7 +142,7 @@ int mmo_render(mmo_render_params *p) {
     closure.pixel_width = p->img_width;
     closure.pixel_height = p->img_height;
     closure.num_args = p->num_uservals;
-    if (p->num_uservals > 32) return -1;
+    if (p->num_uservals > MMO_MAX_ARGS) return -1;
     for (i = 0; i < p->num_uservals; ++i) closure.args[i] = p->uservals[i];
 
     mmo_pools_init(&frame_pools);

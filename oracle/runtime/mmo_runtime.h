@@ -69,6 +69,7 @@ typedef void (*mmo_calc_lines_func)(struct mmo_invocation *, struct mmo_image *c
                                     int region_x, int region_y, int region_w, int region_h, float off_x, float off_y,
                                     int first_row, int last_row, void *q, int floatmap);
 
+#define MMO_MAX_ARGS 96 /* arguments of one filter or closure (a composition of Droste + two more nodes has 37) */
 typedef struct mmo_image {
     int type;
     int pixel_width, pixel_height;
@@ -84,7 +85,7 @@ typedef struct mmo_image {
     mmo_calc_lines_func calc_lines;
     void *xy_vars;
     int num_args;
-    mmo_userval args[32];
+    mmo_userval args[MMO_MAX_ARGS];
     /* resize */
     struct mmo_image *original;
     float x_factor, y_factor;

@@ -52,3 +52,18 @@ def test_design_errors():
     with pytest.raises(mb.MathMapError, match="cycle"):
         mb.design_to_source('(design (node :name "a" :type "util_ident" :input-slots (("in" "b" "out")))'
                             ' (node :name "b" :type "util_ident" :input-slots (("in" "a" "out"))) :name "d" :root "a")', EXAMPLES)
+
+
+def test_reference_benchmark_composition_compiles():
+    """"Gaussian Blur -> Spin Zoom -> Droste" (the reference's published compile-time case, TODO:715-720): the inlined blur
+    inside Droste's sampling loop must come out as frame constants (no per-pixel closure), and only the composite gets a
+    kernel -- the node types' own kernels would double the NVRTC time."""
+    design = ('(design (node :name "g" :type "blur_gauss" :input-slots ())'
+              ' (node :name "s" :type "spin_zoom" :input-slots (("in" "g" "out")))'
+              ' (node :name "d" :type "droste" :input-slots (("in" "s" "out"))) :name "blur_spin_droste" :root "d")')
+    m = mb.Module(source=mb.design_to_source(design, EXAMPLES))
+    closures = [l for l in m.ir.splitlines() if "(closure gaussian_blur" in l]
+    assert closures and all(re.search(r"\(assign %\S+ 7 0 \(closure", l) for l in closures), closures
+    src = m.cuda_source
+    assert "mm_kernel_blur_spin_droste(" in src and "mm_kernel_droste(" not in src and "mm_kernel_spin_zoom(" not in src
+    assert m.compile_check(antialiasing=True) > 0

@@ -447,6 +447,36 @@ def test_every_example_design_matches_oracle(rel):
     assert exact >= 99.9, "%s: %.4f %% exact, %.4f %% within 1 LSB, max %d" % (rel, exact, le1, mx)
 
 
+BENCHMARK_COMPOSITION = """(design
+ (node :name "g" :type "blur_gauss" :input-slots ())
+ (node :name "s" :type "spin_zoom" :input-slots (("in" "g" "out")))
+ (node :name "d" :type "droste" :input-slots (("in" "s" "out")))
+ :name "blur_spin_droste" :root "d")"""
+
+
+@pytest.mark.gpu
+def test_reference_benchmark_composition_matches_oracle():
+    """"Gaussian Blur -> Spin Zoom -> Droste", the composition the reference's only published timings are about
+    (TODO:715-720).  Droste samples its input inside a loop under per-pixel conditions; the inlined blur's
+    gaussian_blur() there has frame-constant arguments behind frame-constant `if`s, so the blur is a frame constant (one
+    native call, cached) and not a closure built per pixel."""
+    import os
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "filters", "examples")
+    m = mb.Module(source=mb.design_to_source(BENCHMARK_COMPOSITION, root))
+    assert m.name == "blur_spin_droste"
+    img = synthetic_rgba(128, 96)
+    for aa in (True, False):
+        inv = mb.Invocation(m, 128, 96, antialiasing=aa)
+        vals = {"g_in": img, "g_dev": 0.02, "s_samples": 5, "d_NoTransparency": 1}
+        for k, v in vals.items():
+            inv.set(k, v)
+        got = inv.render(0, 0.25)
+        want = OracleFilter(m.ir).render(128, 96, vals, t=0.25, antialiasing=aa)
+        exact, le1, mx = compare_u8(got, want)
+        assert exact >= 99.9, "aa=%s: %.4f %% exact, %.4f %% within 1 LSB, max %d" % (aa, exact, le1, mx)
+        assert got[..., :3].std() > 1.0
+
+
 CLOSURE_DISPATCH_SRC = """
 filter inner (image in, float gain: 0-2 (1))
     p = in(xy * 0.9);
