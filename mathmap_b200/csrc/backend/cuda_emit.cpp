@@ -369,7 +369,9 @@ struct Emitter {
                 int t = callee->uservals[i].type;
                 s += ", " + ((t == UV_FLOAT) ? as_float(r->args[i]) : prim(r->args[i]));
             }
-            s += ", " + as_float(r->args[nuv]) + ", " + as_float(r->args[nuv + 1]) + ", " + as_float(r->args[nuv + 2]) + ")";
+            // the nesting level travels with the call: recursion depth is the filter's data (IFS Functional's `depth`), the
+            // device stack is not the host's -- see MM_MAX_CALL_DEPTH in mm_runtime.cuh
+            s += ", " + as_float(r->args[nuv]) + ", " + as_float(r->args[nuv + 1]) + ", " + as_float(r->args[nuv + 2]) + (mode == CALL ? ", mm_depth + 1)" : ", 0)");
             return s;
         }
         case RHS_CLOSURE: unsupported("an image closure that is not frame-constant");
@@ -922,9 +924,10 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
             }
             sig << ", " << ct << " a" << u.index;
         }
-        sig << ", float x, float y, float t)";
+        sig << ", float x, float y, float t, int mm_depth)";
         protos << sig.str() << ";\n";
-        calls << sig.str() << " {\n    const int frame = 0;\n    (void)frame;\n    mm_tup<4> mm_ret = mm_tup<4>{};\n"
+        calls << sig.str() << " {\n    if (mm_depth >= MM_MAX_CALL_DEPTH) { mm_call_overflow = 1; return mm_tup<4>{}; }\n"
+              << "    const int frame = 0;\n    (void)frame;\n    mm_tup<4> mm_ret = mm_tup<4>{};\n"
               << "    unsigned mm_rng = mm_rng_seed(__float_as_int(x), __float_as_int(y), __float_as_int(t)); (void)mm_rng;\n";
         for (const Value *v : decls) calls << "    " << Emitter::ctype(v->cv) << " " << Emitter::vname(v) << ";\n";
         calls << e.out.str() << "    return mm_ret;\n}\n";
@@ -933,6 +936,8 @@ CudaModuleSource emit_cuda_module(const mmb_module &m) {
     }
 
     text << "// generated by mathmap_b200 backend/cuda_emit.cpp\n";
+    src.has_calls = !emitted_calls.empty();
+    if (src.has_calls) text << "__device__ int mm_call_overflow;  // set when a filter call nests deeper than MM_MAX_CALL_DEPTH; read by the host after the launch\n";
     text << protos.str();
     for (auto &b : bodies) text << b;
     text << calls.str();

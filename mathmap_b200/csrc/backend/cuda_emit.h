@@ -46,6 +46,7 @@ struct FilterKernel {
 struct CudaModuleSource {
     std::string text;                                  // generated part (prepended with the runtime by the NVRTC driver)
     std::map<const mm::Filter *, FilterKernel> kernels;  // every mathmap filter that can be rendered
+    bool has_calls = false;  // the module calls filters as device functions (recursion): device stack limit, depth guard (mm_call_overflow)
 };
 
 // Throws mm::CompileError when the IR uses something the device cannot do.

@@ -668,6 +668,16 @@ void launch_filter(mmb_invocation *inv, const Filter *f, const FrameData &fd, co
     if (rc != 0) fail("cuLaunchKernel(" + k.kernel_name + ") failed: " + api->error_string(rc));
     inv->launches++;
     inv->kernel_name = k.kernel_name;
+    if (lm->call_overflow) {  // modules with filter calls (recursion) only: did a call nest deeper than the device stack allows?
+        int flag = 0;
+        cudaError_t e = cudaMemcpyAsync(&flag, lm->call_overflow, sizeof flag, cudaMemcpyDeviceToHost, inv->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(inv->stream);
+        if (e != cudaSuccess) fail(std::string("filter kernel failed: ") + cudaGetErrorString(e));
+        if (flag) {
+            cudaMemsetAsync(lm->call_overflow, 0, sizeof flag, inv->stream);
+            fail("filter " + f->name + ": calls nested deeper than " + std::to_string(MM_MAX_CALL_DEPTH) + " levels (the device stack holds that many frames)");
+        }
+    }
 }
 
 int Replay::render_image(int idx, int width, int height, bool force) {

@@ -32,6 +32,8 @@ struct DriverApi {
     typedef int (*LaunchKernel)(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned smem, void *stream,
                                 void **params, void **extra);
     typedef int (*GetErrorString)(int err, const char **str);
+    typedef int (*ModuleGetGlobal)(unsigned long long *dptr, size_t *bytes, void *module, const char *name);
+    ModuleGetGlobal module_get_global = nullptr;
     ModuleLoadData module_load_data = nullptr;
     ModuleGetFunction module_get_function = nullptr;
     ModuleUnload module_unload = nullptr;
@@ -46,6 +48,7 @@ struct LoadedModule {
     void *module = nullptr;
     std::map<const mm::Filter *, void *> functions;
     std::map<const mm::Filter *, void *> row_functions;  // row pre-kernels (absent when a filter has none)
+    void *call_overflow = nullptr;                       // device address of mm_call_overflow (modules with filter calls)
     ~LoadedModule();
 };
 

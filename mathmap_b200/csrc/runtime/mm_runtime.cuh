@@ -36,6 +36,11 @@
 #endif
 
 #define MM_DEV __device__ __forceinline__
+// Filters that call filters which cannot be inlined (recursion) run as device functions, one stack frame per level (about
+// 100-250 bytes).  The host raises the device stack limit to 16 KB per thread for such modules; a call nested deeper than
+// this returns transparent black and sets mm_call_overflow, which the host turns into an error -- instead of a stack
+// overrun that would take the CUDA context with it.  (The deepest range an example declares is IFS Functional's 1-32.)
+// MM_MAX_CALL_DEPTH: mm_types.h (the host names it in its error message)
 
 // Pixel-grid launch geometry: 1-D blocks of 256 threads, each block renders a
 // 32 x 8 pixel tile; MM_WARP_W selects the footprint of one warp inside the tile

@@ -27,6 +27,10 @@ struct mm_image {
     int closure_filter;    // MM_IMAGE_CLOSURE: which filter; `data` then points at that filter's packed uniforms (device memory)
 };
 
+#ifndef MM_MAX_CALL_DEPTH
+#define MM_MAX_CALL_DEPTH 64 /* nesting levels of filter calls on the device, see mm_runtime.cuh */
+#endif
+
 // Per-launch parameters (the invocation / frame / slice fields calc_lines reads,
 // reference mathmap.h:161-227, new_template.c.in:210-234).
 struct mm_params {

@@ -477,6 +477,47 @@ def test_reference_benchmark_composition_matches_oracle():
         assert got[..., :3].std() > 1.0
 
 
+RECURSIVE_SRC = """
+filter rec (image in, int depth: 1-200 (3))
+  if depth < 2 then in(xy) else rec(in, depth - 1, xy * 0.99) * 0.99 end
+end
+"""
+
+
+@pytest.mark.gpu
+def test_deep_filter_recursion_is_bounded_not_fatal():
+    """Filter calls that cannot be inlined (recursion) run as device functions, one stack frame per level: the default CUDA
+    stack (1 KB per thread) held IFS Functional's default depth 8 but not 14 -- an illegal address that took the context with
+    it.  The backend raises the stack limit for such modules, carries the nesting level through the calls and turns a call
+    deeper than MM_MAX_CALL_DEPTH (64) into an error; the full declared range of the example (1-32) renders like the oracle."""
+    img = synthetic_rgba(64, 48)
+    m = mb.Module(source=filter_source("examples/Map/IFS Functional.mm"))
+    inv = mb.Invocation(m, 64, 48, antialiasing=True)
+    oracle = OracleFilter(m.ir)
+    for depth in (14, 32):
+        vals = {"in": img, "depth": depth, "factor": 0.9, "angle": 0.1}
+        for k, v in vals.items():
+            inv.set(k, v)
+        got = inv.render(0, 0.0)
+        want = oracle.render(64, 48, vals, t=0.0, antialiasing=True)
+        exact, le1, mx = compare_u8(got, want)
+        assert exact >= 99.9, "depth %d: %.4f %% exact, %.4f %% within 1 LSB, max %d" % (depth, exact, le1, mx)
+    m2 = mb.Module(source=RECURSIVE_SRC)
+    inv2 = mb.Invocation(m2, 64, 48, antialiasing=False)
+    inv2.set("in", img)
+    inv2.set("depth", 60)
+    got = inv2.render(0, 0.0)
+    want = OracleFilter(m2.ir).render(64, 48, {"in": img, "depth": 60}, t=0.0, antialiasing=False)
+    assert compare_u8(got, want)[0] >= 99.9
+    inv2.set("depth", 150)
+    with pytest.raises(mb.MathMapError, match="nested deeper than 64 levels"):
+        inv2.render(0, 0.0)
+    inv2.set("depth", 5)  # the context survived, the flag is cleared
+    got = inv2.render(0, 0.0)
+    want = OracleFilter(m2.ir).render(64, 48, {"in": img, "depth": 5}, t=0.0, antialiasing=False)
+    assert compare_u8(got, want)[0] >= 99.9
+
+
 CLOSURE_DISPATCH_SRC = """
 filter inner (image in, float gain: 0-2 (1))
     p = in(xy * 0.9);
