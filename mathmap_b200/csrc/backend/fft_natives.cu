@@ -146,9 +146,10 @@ __global__ void __launch_bounds__(256) floatmap_resample_kernel(const float4 *sr
     if (x >= width || y >= height) return;
     float fx = __fmul_rn(__fdiv_rn(__fsub_rn((float)x, bx), ax), xf), fy = __fmul_rn(__fdiv_rn(__fsub_rn((float)y, by), ay), yf);
     float px = __fadd_rn(__fmul_rn(sax, fx), sbx), py = __fadd_rn(__fmul_rn(say, fy), sby);
-    float rx = rintf(px), ry = rintf(py);
+    // (int)lrintf(), x86-64: NaN and |v| >= 2^63 become 0, otherwise the low 32 bits of the rounded value (mm_runtime.cuh: mm_lrintf_to_int)
+    const int rx = fabsf(px) < 9223372036854775808.0f ? (int)__float2ll_rn(px) : 0, ry = fabsf(py) < 9223372036854775808.0f ? (int)__float2ll_rn(py) : 0;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rx >= 0.0f && rx < (float)sw && ry >= 0.0f && ry < (float)sh) v = src[(size_t)(int)ry * sw + (int)rx];
+    if (rx >= 0 && rx < sw && ry >= 0 && ry < sh) v = src[(size_t)ry * sw + rx];
     out[(size_t)y * width + x] = v;
 }
 

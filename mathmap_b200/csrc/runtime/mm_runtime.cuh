@@ -513,19 +513,25 @@ MM_DEV mm_tup<4> mm_apply_gradient(const mm_color *grad, float p) {
 }
 
 // --------------------------------------------------------------------- sampling
+// builtins/builtins.c:41-119 (C remainder semantics == CUDA's).  A NaN or out-of-range coordinate arrives here as INT_MIN
+// (the x86 conversion, mm_f2i), and the reference then negates it or subtracts it from width - 1: signed overflow, undefined
+// in C and in CUDA C++ alike -- gcc -O2 and NVVM both conclude "the result of -x % width lies in [0, width)", drop the
+// range check that follows, and the reference reads a texel row 32 rows in front of the image.  Here the negation and the
+// subtraction wrap (unsigned arithmetic), INT_MIN stays negative or becomes 0, and the range check holds.
+MM_DEV int mm_wrap_neg(int v) { return (int)(0u - (unsigned)v); }
+MM_DEV int mm_wrap_sub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 template <int MODE_X, int MODE_Y> MM_DEV void mm_apply_edge_behaviour(int &x, int &y, int width, int height) {
-    // builtins/builtins.c:41-119 (C remainder semantics == CUDA's)
     if (MODE_X == 1) { if (x < 0) x = x % width + width; else if (x >= width) x %= width; }
-    else if (MODE_X == 2) { if (x < 0) x = -x % width; else if (x >= width) x = (width - 1) - (x % width); }
+    else if (MODE_X == 2) { if (x < 0) x = mm_wrap_neg(x) % width; else if (x >= width) x = (width - 1) - (x % width); }
     else if (MODE_X == 3) {
-        if (x < 0) { x = -x % width; y = (height - 1) - y; }
-        else if (x >= width) { x = (width - 1) - (x % width); y = (height - 1) - y; }
+        if (x < 0) { x = mm_wrap_neg(x) % width; y = mm_wrap_sub(height - 1, y); }
+        else if (x >= width) { x = (width - 1) - (x % width); y = mm_wrap_sub(height - 1, y); }
     }
     if (MODE_Y == 1) { if (y < 0) y = y % height + height; else if (y >= height) y %= height; }
-    else if (MODE_Y == 2) { if (y < 0) y = -y % height; else if (y >= height) y = (height - 1) - (y % height); }
+    else if (MODE_Y == 2) { if (y < 0) y = mm_wrap_neg(y) % height; else if (y >= height) y = (height - 1) - (y % height); }
     else if (MODE_Y == 3) {
-        if (y < 0) { x = (width - 1) - x; y = -y % height; }
-        else if (y >= height) { x = (width - 1) - x; y = (height - 1) - (y % height); }
+        if (y < 0) { x = mm_wrap_sub(width - 1, x); y = mm_wrap_neg(y) % height; }
+        else if (y >= height) { x = mm_wrap_sub(width - 1, x); y = (height - 1) - (y % height); }
     }
 }
 
@@ -745,11 +751,15 @@ MM_DEV bool mm_nearest_exterior(const mm_params &P, const mm_image &img, float x
     return false;
 }
 
+// (int)lrintf(v) as the reference's x86-64 build computes it (builtins.c:257-258): cvtss2si into a 64-bit long -- NaN and
+// |v| >= 2^63 give 0x8000000000000000 -- of which the cast keeps the low 32 bits.  So a NaN coordinate reads column / row 0
+// (not "out of range" as the 32-bit conversions of the drawable samplers make it), and so do 2^32, 2^33 ...
+MM_DEV int mm_lrintf_to_int(float v) { return fabsf(v) < 9223372036854775808.0f ? (int)__float2ll_rn(v) : 0; }
 // get_floatmap_pixel, builtins.c:249-265: nearest via lrintf (round half even)
 MM_DEV mm_tup<4> mm_floatmap_pixel(const mm_image &img, float x, float y) {
     mm_tup<4> t;
     float fx = __fadd_rn(__fmul_rn(img.ax, x), img.bx), fy = __fadd_rn(__fmul_rn(img.ay, y), img.by);
-    int ix = mm_f2i(rintf(fx)), iy = mm_f2i(rintf(fy));
+    int ix = mm_lrintf_to_int(fx), iy = mm_lrintf_to_int(fy);
     if (ix < 0 || ix >= img.w || iy < 0 || iy >= img.h) { t.v[0] = t.v[1] = t.v[2] = t.v[3] = 0.0f; return t; }
     float4 v = __ldg((const float4 *)img.data + ((size_t)iy * (size_t)img.w + (size_t)ix));
     t.v[0] = v.x; t.v[1] = v.y; t.v[2] = v.z; t.v[3] = v.w;

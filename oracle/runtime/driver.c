@@ -82,6 +82,10 @@ static void call_invocation(band_t *b) {
         unsigned char *q = b->q;
         mmo_main_calc_lines(inv, b->closure, b->xy_vars, b->frame, b->t, W, H, b->region_x, b->region_y, b->region_width + 1,
                             b->region_height, -0.5f, -0.5f, b->region_y, b->region_y + 1, line1, 0);
+        /* a region of ONE row never writes line3 in the reference (its only line3 call is clamped away, see below) and the
+         * combine reads uninitialised heap memory there; the oracle and the CUDA path define it as line1, what line3 holds at
+         * the last row of every taller region */
+        memcpy(line3, line1, (b->region_width + 1) * bpp);
         for (row = b->region_y; row < b->region_y + b->region_height; ++row) {
             unsigned char *p = q;
             mmo_main_calc_lines(inv, b->closure, b->xy_vars, b->frame, b->t, W, H, b->region_x, b->region_y, b->region_width,

@@ -45,6 +45,14 @@ mmo_image *mmo_make_resize_image(mmo_image *image, float x_factor, float y_facto
     return r;
 }
 
+/* builtins/builtins.c:41-119.  One deliberate difference: a NaN or out-of-range coordinate arrives as INT_MIN (the x86
+ * conversion), and the reference negates it / subtracts it from width - 1 -- signed overflow, undefined behaviour.  gcc -O2
+ * concludes that -x % width lies in [0, width), drops the range check in get_pixel, and the reference reads a texel row in
+ * front of the image (seen with Droste's NaN coordinates under the reflect / rotate modes).  No result can be "identical" to
+ * that; the oracle and the CUDA path both let these two operations wrap, so INT_MIN stays out of range and yields the edge
+ * colour (or texel 0 when width is a power of two). */
+static int wrap_neg(int v) { return (int)(0u - (unsigned)v); }
+static int wrap_sub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 static void apply_edge_behaviour(mmo_invocation *invocation, int *_x, int *_y, int width, int height) {
     int x = *_x, y = *_y;
     switch (invocation->edge_behaviour_x) {
@@ -53,12 +61,12 @@ static void apply_edge_behaviour(mmo_invocation *invocation, int *_x, int *_y, i
         else if (x >= width) x %= width;
         break;
     case EDGE_BEHAVIOUR_REFLECT:
-        if (x < 0) x = -x % width;
+        if (x < 0) x = wrap_neg(x) % width;
         else if (x >= width) x = (width - 1) - (x % width);
         break;
     case EDGE_BEHAVIOUR_ROTATE:
-        if (x < 0) { x = -x % width; y = (height - 1) - y; }
-        else if (x >= width) { x = (width - 1) - (x % width); y = (height - 1) - y; }
+        if (x < 0) { x = wrap_neg(x) % width; y = wrap_sub(height - 1, y); }
+        else if (x >= width) { x = (width - 1) - (x % width); y = wrap_sub(height - 1, y); }
         break;
     default: break;
     }
@@ -68,12 +76,12 @@ static void apply_edge_behaviour(mmo_invocation *invocation, int *_x, int *_y, i
         else if (y >= height) y %= height;
         break;
     case EDGE_BEHAVIOUR_REFLECT:
-        if (y < 0) y = -y % height;
+        if (y < 0) y = wrap_neg(y) % height;
         else if (y >= height) y = (height - 1) - (y % height);
         break;
     case EDGE_BEHAVIOUR_ROTATE:
-        if (y < 0) { x = (width - 1) - x; y = -y % height; }
-        else if (y >= height) { x = (width - 1) - x; y = (height - 1) - (y % height); }
+        if (y < 0) { x = wrap_sub(width - 1, x); y = wrap_neg(y) % height; }
+        else if (y >= height) { x = wrap_sub(width - 1, x); y = (height - 1) - (y % height); }
         break;
     default: break;
     }
