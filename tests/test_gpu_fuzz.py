@@ -29,8 +29,10 @@ def test_random_arguments_match_oracle(seed, count, only, settings):
 WILD_COORDINATES = {
     "nan_x": "filter z (image in)\n  in(xy:[log(abs(x)-0.5), y])\nend\n",
     "nan_y": "filter z (image in)\n  in(xy:[x, sqrt(y)])\nend\n",
-    "huge": "filter z (image in)\n  in(xy:[x*1e30*(y+0.3), y*3e9])\nend\n",
-    "around_2_31": "filter z (image in)\n  in(xy:[x*4.4e7, y*2.2e9+x*1e5])\nend\n",
+    # (the language has no exponent notation, scanner.c:286-336)
+    "huge": "filter z (image in)\n  in(xy:[x*1000000000000000000000000000000.0*(y+0.3), y*3000000000.0])\nend\n",
+    "around_2_31": "filter z (image in)\n  in(xy:[x*44000000.0, y*2200000000.0+x*100000.0])\nend\n",
+    "around_2_32": "filter z (image in)\n  c = in(xy:[x*4294967296.0/(W/2), y*8589934592.0/(H/2)]);\n  rgba:[1-c[0], c[1], c[2]*0.5, c[3]]\nend\n",
 }
 
 
@@ -92,3 +94,12 @@ def test_one_pixel_wide_frames(rel):
                     assert np.allclose(got, want, rtol=1e-5, atol=1e-6, equal_nan=True), (rel, w, h, aa)
                 else:
                     assert np.array_equal(got, want), (rel, w, h, aa)
+
+
+@pytest.mark.gpu
+def test_random_slices_equal_the_whole_frame():
+    """mmb_calc_lines_slice (the reference's calc_lines parameters: region, row range, row stride) with random values against
+    the same pixels of the whole frame; bytes between rows and behind the last one stay untouched (tools/fuzz_slices.py)."""
+    import fuzz_slices
+    cases, failures = fuzz_slices.run(5, 150)
+    assert not failures, failures
