@@ -80,6 +80,12 @@ int mmb_set_rows_per_thread(mmb_invocation *inv, int rows); /* 32x8 tiles one bl
  * (`if (userval)`: the reference's init_frame values, new_template.c.in:314-337, as compile-time constants), one NVRTC
  * compile per combination actually used; 0: one kernel that tests them per pixel */
 int mmb_set_specialize(mmb_invocation *inv, int enabled);
+/* 0 (default): every device function inlined into the pixel kernel; 1: the complex elementary functions (cexpf, clogf,
+ * cpowf, csinf ...: the largest bodies of the device runtime) are real calls, compiled once per module instead of once per
+ * call site -- Map/Droste: NVRTC 3.7 -> 2.1 s, kernel 4-5 % slower, same bits.  For callers that show the first frame
+ * of a newly edited filter (the reference's only published timings are compile times: TODO:715-720); kernels of both kinds
+ * are cached side by side */
+int mmb_set_fast_compile(mmb_invocation *inv, int enabled);
 int mmb_set_precise_math(mmb_invocation *inv, int enabled);   /* 1 (default): libm calls evaluated in double and narrowed, like the host; 0: CUDA float libm (<= 2 ulp, faster) */
 
 /* userval bindings, reference userval.h userval_t / mathmap_cmdline.c:756-796 (-D name=value) */
@@ -156,6 +162,7 @@ int mmb_gaussian_blur_device(int device, const float *device_in, float *device_o
 
 /* NVRTC-compiles the module for sm_100a without needing a GPU (build check); returns cubin bytes or -1 */
 long mmb_module_compile_check(mmb_module *m, int antialiasing, int precise_math);
+long mmb_module_compile_check_fast(mmb_module *m, int antialiasing, int precise_math); /* the same with mmb_set_fast_compile(1) */
 /* Optional persistent cubin cache, process-wide: with a directory set, compiled kernels are stored there under a key of the
  * NVRTC version, options, device runtime and generated source, and loaded instead of recompiled by later processes.  The
  * reference has no equivalent (gcc runs on every load of a filter, backends/cc.c:634-758).  NULL or "" turns it off (default). */

@@ -50,11 +50,11 @@ def lib():
         "mmb_module_num_uservals": (ci, [vp]),
         "mmb_module_userval_info": (ci, [vp, ci, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ci), ctypes.POINTER(cf), ctypes.POINTER(cf), ctypes.POINTER(cf)]),
         "mmb_module_userval_index": (ci, [vp, cc]),
-        "mmb_module_compile_check": (ctypes.c_long, [vp, ci, ci]), "mmb_set_cubin_cache_dir": (ci, [ctypes.c_char_p]),
+        "mmb_module_compile_check": (ctypes.c_long, [vp, ci, ci]), "mmb_module_compile_check_fast": (ctypes.c_long, [vp, ci, ci]), "mmb_set_cubin_cache_dir": (ci, [ctypes.c_char_p]),
         "mmb_invoke": (vp, [vp, ci, ci, ci]), "mmb_invocation_free": (None, [vp]),
         "mmb_set_antialiasing": (ci, [vp, ci]), "mmb_set_supersampling": (ci, [vp, ci]),
         "mmb_set_edge_behaviour": (ci, [vp, ci, ci, ctypes.c_uint32, ctypes.c_uint32]),
-        "mmb_set_output_bpp": (ci, [vp, ci]), "mmb_set_precise_math": (ci, [vp, ci]), "mmb_set_warp_shape": (ci, [vp, ci]), "mmb_set_specialize": (ci, [vp, ci]), "mmb_set_rows_per_thread": (ci, [vp, ci]),
+        "mmb_set_output_bpp": (ci, [vp, ci]), "mmb_set_precise_math": (ci, [vp, ci]), "mmb_set_warp_shape": (ci, [vp, ci]), "mmb_set_specialize": (ci, [vp, ci]), "mmb_set_fast_compile": (ci, [vp, ci]), "mmb_set_rows_per_thread": (ci, [vp, ci]),
         "mmb_set_userval_int": (ci, [vp, ci, ci]), "mmb_set_userval_float": (ci, [vp, ci, cf]), "mmb_set_userval_bool": (ci, [vp, ci, ci]),
         "mmb_set_userval_color": (ci, [vp, ci, cf, cf, cf, cf]),
         "mmb_set_userval_color_packed": (ci, [vp, ci, ctypes.c_uint32]),
@@ -164,9 +164,10 @@ class Module:
             out.append((name.value.decode(), t.value, lo.value, hi.value, d.value))
         return out
 
-    def compile_check(self, antialiasing=True, precise=False):
+    def compile_check(self, antialiasing=True, precise=False, fast_compile=False):
         """NVRTC-compiles for sm_100a (no GPU needed); returns the cubin size."""
-        n = lib().mmb_module_compile_check(self._h, int(antialiasing), int(precise))
+        fn = lib().mmb_module_compile_check_fast if fast_compile else lib().mmb_module_compile_check
+        n = fn(self._h, int(antialiasing), int(precise))
         if n < 0:
             raise MathMapError(_err())
         return n
@@ -176,7 +177,7 @@ class Invocation:
     """reference: mathmap_invocation_t from invoke_mathmap (mathmap_common.c:747)."""
 
     def __init__(self, module, width, height, device=0, antialiasing=False, supersampling=False, precise=True, warp_width=None, rows_per_thread=None,
-                 specialize=None):
+                 specialize=None, fast_compile=None):
         self.module = module
         self.width, self.height = width, height
         self.bpp = 4
@@ -194,6 +195,8 @@ class Invocation:
             self._ck(lib().mmb_set_rows_per_thread(self._h, rows_per_thread))
         if specialize is not None:
             self._ck(lib().mmb_set_specialize(self._h, int(specialize)))
+        if fast_compile is not None:
+            self._ck(lib().mmb_set_fast_compile(self._h, int(fast_compile)))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

@@ -47,6 +47,7 @@ def main(argv=None):
     ap.add_argument("--bench-no-backend", action="store_true")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--fast-math", action="store_true")
+    ap.add_argument("--fast-compile", action="store_true", help="shorter filter compile, a few percent slower kernel (mmb_set_fast_compile)")
     ap.add_argument("--filter-path", default=None, help="directory tree searched for the node types of a .mmc composition")
     ap.add_argument("--version", action="store_true")
     ap.add_argument("rest", nargs="*")
@@ -112,7 +113,7 @@ def main(argv=None):
         return 1
     try:
         inv = mb.Invocation(module, size[0], size[1], device=a.device, antialiasing=a.intersampling, supersampling=a.oversampling,
-                            precise=not a.fast_math)
+                            precise=not a.fast_math, fast_compile=a.fast_compile)
         for k, v in defines.items():
             inv.set(k, v)
         for _ in range(max(1, a.bench_render_count)):

@@ -1014,6 +1014,18 @@ long mmb_module_compile_check(mmb_module *m, int antialiasing, int precise_math)
     return n;
 }
 
+long mmb_module_compile_check_fast(mmb_module *m, int antialiasing, int precise_math) {
+    if (!m) return -1;
+    KernelConfig cfg;
+    cfg.aa = antialiasing;
+    cfg.precise = precise_math;
+    cfg.fast_compile = 1;
+    std::string err;
+    long n = compile_only(m, cfg, err);
+    if (n < 0) set_error(err);
+    return n;
+}
+
 mmb_invocation *mmb_invoke(mmb_module *m, int img_width, int img_height, int device) {
     if (!m || img_width <= 0 || img_height <= 0) { set_error("mmb_invoke: bad arguments"); return nullptr; }
     auto inv = new mmb_invocation();
@@ -1123,6 +1135,11 @@ int mmb_set_render_size(mmb_invocation *inv, int render_width, int render_height
 int mmb_set_specialize(mmb_invocation *inv, int enabled) {
     if (!inv) return -1;
     inv->cfg.specialize = enabled ? 1 : 0;
+    return 0;
+}
+int mmb_set_fast_compile(mmb_invocation *inv, int enabled) {
+    if (null_inv(inv, "mmb_set_fast_compile")) return -1;
+    inv->cfg.fast_compile = enabled ? 1 : 0;
     return 0;
 }
 int mmb_set_warp_shape(mmb_invocation *inv, int warp_width) {

@@ -20,6 +20,7 @@ struct KernelConfig {
     int rows = 0;  // 32x8 tiles a block renders in sequence (a launch parameter, not part of the key); 0 = chosen per launch
     int specialize = 1;  // compile the main filter's kernel for the frame-constant branch conditions of the frame (not part of the key)
     std::string spec;    // "#define MM_SPEC_<filter>_<i> 0|1" lines (FilterKernel::spec_conds), part of the key
+    int fast_compile = 0;  // the complex elementary functions as real calls (MM_COMPLEX_CALLS, mm_runtime.cuh): shorter compile, slower kernel; part of the key
     std::string key() const;
 };
 

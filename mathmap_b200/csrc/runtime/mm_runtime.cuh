@@ -267,6 +267,18 @@ MM_DEV mm_cd mm_cd_sqrt(mm_cd z) {
 }
 MM_DEV mm_cd mm_cd_make(double re, double im) { mm_cd r; r.re = re; r.im = im; return r; }
 
+// The complex elementary functions are the largest bodies of the runtime (double exp, sincos with range reduction, the log1p
+// branches of clogf ...), and a filter like Droste names them at a dozen sites.  MM_COMPLEX_CALLS = 1 makes them real
+// calls: compiled once per module instead of once per site (Droste: NVRTC 3.6 -> 2.0 s); the NVRTC driver sets it for
+// modules with many such sites (nvrtc_module.cpp).  Results are the same bits either way.
+#ifndef MM_COMPLEX_CALLS
+#define MM_COMPLEX_CALLS 0
+#endif
+#if MM_COMPLEX_CALLS
+#define MM_CFN __device__ __noinline__
+#else
+#define MM_CFN MM_DEV
+#endif
 MM_DEV float2 mm_complex(float re, float im) { return make_float2(re, im); }
 MM_DEV float mm_creal(float2 z) { return z.x; }
 MM_DEV float mm_cimag(float2 z) { return z.y; }
@@ -290,7 +302,7 @@ MM_DEV void mm_cr_sincos(float x, float &s, float &c) {  // glibc: sincosf unles
     if (fabsf(x) > MM_FLT_MIN) mm_sincos(x, s, c);
     else { s = x; c = 1.0f; }
 }
-MM_DEV float2 mm_csqrt(float2 z) {
+MM_CFN float2 mm_csqrt(float2 z) {
     // s_csqrt_template.c; the range-scaling branches (|z| > FLT_MAX/4, subnormal parts) take the double formula
     const float ax = fabsf(z.x), ay = fabsf(z.y);
     if (!mm_c_finite(z) || ax > 8.5e37f || ay > 8.5e37f || (ax < 2.0f * MM_FLT_MIN && ax != 0.0f) || (ay < 2.0f * MM_FLT_MIN && ay != 0.0f))
@@ -314,7 +326,7 @@ MM_DEV float2 mm_csqrt(float2 z) {
     }
     return make_float2(r, copysignf(sgn, z.y));
 }
-MM_DEV float2 mm_cexp(float2 z) {
+MM_CFN float2 mm_cexp(float2 z) {
     // glibc cexpf: expf(re) * (cosf(im), sinf(im)), each factor rounded to float first
     float e = mm_exp(z.x), s, c;
     mm_sincos(z.y, s, c);  // each equals the separately evaluated sinf / cosf
@@ -322,7 +334,7 @@ MM_DEV float2 mm_cexp(float2 z) {
 }
 // logf, correctly rounded, in both math modes (the argument is positive and finite here)
 MM_DEV float mm_log_cr(float a) { return (a > 0.0f && a < __int_as_float(0x7f800000)) ? mm_d_log_core(a) : (float)log((double)a); }
-MM_DEV float2 mm_clog(float2 z) {
+MM_CFN float2 mm_clog(float2 z) {
     // s_clog_template.c without its scaling of huge / subnormal arguments
     float ax = fabsf(z.x), ay = fabsf(z.y);
     if (!mm_c_finite(z) || (ax == 0.0f && ay == 0.0f) || ax > 1.7e38f || ay > 1.7e38f || (ax < MM_FLT_MIN && ay < MM_FLT_MIN))
@@ -346,7 +358,7 @@ MM_DEV float2 mm_clog(float2 z) {
     return make_float2(re, mm_g_atan2f(z.y, z.x));
 }
 MM_DEV float mm_carg(float2 z) { return mm_g_atan2f(z.y, z.x); }  // cargf = atan2f, ops.lisp:205
-MM_DEV float2 mm_cpow(float2 a, float2 b) {
+MM_CFN float2 mm_cpow(float2 a, float2 b) {
     // glibc cpowf(x, c) = cexpf(c * clogf(x)) in float complex arithmetic
     float2 l = mm_clog(a);
     return mm_cexp(mm_cmul(b, l));
@@ -362,7 +374,7 @@ MM_DEV float2 mm_csinh_core(float re, float im) {
     mm_cr_sincos(im, s, c);
     return make_float2(__fmul_rn(mm_cr_sinh(re), c), __fmul_rn(mm_cr_cosh(re), s));
 }
-MM_DEV float2 mm_csin(float2 z) {
+MM_CFN float2 mm_csin(float2 z) {
     if (mm_c_finite(z) && fabsf(z.y) <= 88.0f) {  // s_csin_template.c
         float s, c;
         mm_cr_sincos(fabsf(z.x), s, c);
@@ -372,7 +384,7 @@ MM_DEV float2 mm_csin(float2 z) {
     double s, c; sincos((double)z.x, &s, &c);
     return make_float2((float)(s * cosh((double)z.y)), (float)(c * sinh((double)z.y)));
 }
-MM_DEV float2 mm_ccos(float2 z) {
+MM_CFN float2 mm_ccos(float2 z) {
     if (mm_c_finite(z) && fabsf(z.y) <= 88.0f) return mm_ccosh_core(-z.y, z.x);  // ccosf(z) = ccoshf(i z), s_ccos_template.c
     double s, c; sincos((double)z.x, &s, &c);
     return make_float2((float)(c * cosh((double)z.y)), (float)(-s * sinh((double)z.y)));
@@ -388,7 +400,7 @@ MM_DEV float mm_ctan_small_part(float sinu, float cosu, float v) {
     else r = __fdiv_rn(r, (float)exp((double)__fmul_rn(2.0f, v)));
     return r;
 }
-MM_DEV float2 mm_ctan(float2 z) {
+MM_CFN float2 mm_ctan(float2 z) {
     if (mm_c_finite(z)) {  // s_ctan_template.c
         float sinrx, cosrx, sinhix, coshix, den;
         mm_cr_sincos(z.x, sinrx, cosrx);
@@ -403,17 +415,17 @@ MM_DEV float2 mm_ctan(float2 z) {
     double d = c + cosh(2.0 * (double)z.y);
     return make_float2((float)(s / d), (float)(sinh(2.0 * (double)z.y) / d));
 }
-MM_DEV float2 mm_csinh(float2 z) {
+MM_CFN float2 mm_csinh(float2 z) {
     if (mm_c_finite(z) && fabsf(z.x) <= 88.0f) return mm_csinh_core(z.x, z.y);  // s_csinh_template.c
     double s, c; sincos((double)z.y, &s, &c);
     return make_float2((float)(sinh((double)z.x) * c), (float)(cosh((double)z.x) * s));
 }
-MM_DEV float2 mm_ccosh(float2 z) {
+MM_CFN float2 mm_ccosh(float2 z) {
     if (mm_c_finite(z) && fabsf(z.x) <= 88.0f) return mm_ccosh_core(z.x, z.y);  // s_ccosh_template.c
     double s, c; sincos((double)z.y, &s, &c);
     return make_float2((float)(cosh((double)z.x) * c), (float)(sinh((double)z.x) * s));
 }
-MM_DEV float2 mm_ctanh(float2 z) {
+MM_CFN float2 mm_ctanh(float2 z) {
     if (mm_c_finite(z)) {  // s_ctanh_template.c
         float sinix, cosix, sinhrx, coshrx, den;
         mm_cr_sincos(z.y, sinix, cosix);
@@ -770,7 +782,7 @@ MM_DEV mm_tup<4> mm_floatmap_pixel(const mm_image &img, float x, float y) {
 __device__ mm_tup<4> mm_closure_dispatch(const mm_params &P, const mm_image &img, float x, float y, float t);
 
 // ORIG_VAL (opmacros.h:199-216); closures known at compile time are inlined or called directly, the others dispatch
-MM_DEV mm_tup<4> mm_orig_val(const mm_params &P, int image, float x, float y, float t) {
+MM_DEV mm_tup<4> mm_orig_val_full(const mm_params &P, int image, float x, float y, float t) {
     const mm_image &img = P.images[image];
     x = __fmul_rn(x, img.xf);  // 1.0 unless a RESIZE wrapper survived to run time
     y = __fmul_rn(y, img.yf);
@@ -798,7 +810,27 @@ MM_DEV mm_tup<4> mm_orig_val_nearest(const mm_params &P, const mm_image &img, fl
 
 // The general ORIG_VAL as a real call: keeps everything but the interior fast path out of the pixel loop of a
 // direct-output kernel (inlined, its branches cost the hot path about ten instructions of convergence bookkeeping).
-__device__ __noinline__ mm_tup<4> mm_orig_val_call(const mm_params &P, int image, float x, float y, float t) { return mm_orig_val(P, image, x, y, t); }
+__device__ __noinline__ mm_tup<4> mm_orig_val_call(const mm_params &P, int image, float x, float y, float t) { return mm_orig_val_full(P, image, x, y, t); }
+// What generated code calls.  With MM_COMPLEX_CALLS (mmb_set_fast_compile) only a drawable's interior fast path is inlined at
+// a sample site and the rest (floatmaps, closures, border and exterior texels, edge modes) is the one call above.
+MM_DEV mm_tup<4> mm_orig_val(const mm_params &P, int image, float x, float y, float t) {
+#if MM_COMPLEX_CALLS
+    const mm_image &img = P.images[image];
+    if (img.kind == MM_IMAGE_DRAWABLE) {
+        mm_tup<4> r;
+        unsigned unused;
+        const float xs = __fmul_rn(x, img.xf), ys = __fmul_rn(y, img.yf);
+#if MM_AA
+        if (mm_bilinear_interior<false>(P, img, xs, ys, t, r, unused)) return r;
+#else
+        if (mm_nearest_interior<false>(P, img, xs, ys, t, r, unused)) return r;
+#endif
+    }
+    return mm_orig_val_call(P, image, x, y, t);
+#else
+    return mm_orig_val_full(P, image, x, y, t);
+#endif
+}
 
 // ORIG_VAL whose result is the pixel itself (cuda_emit.cpp: find_direct_output).  For RGBA8 output of a drawable's
 // interior the sample's rounded bytes ARE the output bytes: the reference turns byte k into (float)(k / 255.0), clamps,

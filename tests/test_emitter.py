@@ -75,3 +75,14 @@ def test_every_example_filter_compiles_for_sm100a():
         except mb.MathMapError as e:
             failed.append((os.path.relpath(path, FILTERS), str(e).splitlines()[0] if str(e) else "error"))
     assert not failed, failed
+
+
+def test_fast_compile_is_a_different_smaller_kernel():
+    """mmb_set_fast_compile: the complex elementary functions and everything of the samplers but a drawable's interior path as
+    real calls -- one body per module instead of one per call site.  Droste's cubin shrinks by a third (and its NVRTC time by
+    about 45 %: DESIGN.md, filter compile time); a filter without complex functions whose sample is its pixel already calls the
+    general sampler and compiles to the same size."""
+    droste = mb.Module.from_file(os.path.join(FILTERS, "Map/Droste.mm"))
+    assert droste.compile_check(antialiasing=True, precise=True, fast_compile=True) < 0.8 * droste.compile_check(antialiasing=True, precise=True)
+    twirl = mb.Module.from_file(os.path.join(FILTERS, "Distorts/Twirl.mm"))
+    assert twirl.compile_check(antialiasing=True, precise=True, fast_compile=True) == twirl.compile_check(antialiasing=True, precise=True)

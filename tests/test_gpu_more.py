@@ -681,3 +681,23 @@ def test_many_frames_do_not_grow_device_memory():
     free_early = frames(40, 0)
     free_late = frames(360, 40)
     assert free_early - free_late < (8 << 20), "device memory grew by %.1f MiB over 360 frames" % ((free_early - free_late) / 2 ** 20)
+
+
+@pytest.mark.gpu
+def test_fast_compile_kernels_give_the_same_bytes():
+    """mmb_set_fast_compile changes what is inlined, not what is computed: Droste (complex functions, three sample sites with
+    border texels), IFS Functional (recursion through calls and closures), Spin-Zoom (samples in a loop) and a filter of complex
+    functions render the same bytes either way, with both samplers, and into floatmaps."""
+    img = synthetic_rgba(160, 120)
+    cplx = "filter f (image in)\n  lz = ri:[x * 3, y * 3];\n  lw = exp(lz) * 0.1 + log(lz) + sin(lz) * lz ^ ri:[1.5, 0.2] + sqrt(lz) + tan(lz) * 0.01;\n  in(xy:[lw[0] * 0.3, lw[1] * 0.3])\nend\n"
+    sources = [filter_source("examples/Map/Droste.mm"), filter_source("examples/Map/IFS Functional.mm"), filter_source("examples/Blur/Spin-Zoom.mm"), cplx]
+    for src in sources:
+        m = mb.Module(source=src)
+        for aa in (False, True):
+            for floatmap in (False, True):
+                outs = []
+                for fast in (False, True):
+                    inv = mb.Invocation(m, 160, 120, antialiasing=aa, fast_compile=fast)
+                    inv.set("in", img)
+                    outs.append(inv.render(0, 0.3, floatmap=floatmap))
+                assert np.array_equal(outs[0].view(np.uint8), outs[1].view(np.uint8)), (m.name, aa, floatmap)
