@@ -766,7 +766,10 @@ MM_DEV bool mm_nearest_exterior(const mm_params &P, const mm_image &img, float x
 // (int)lrintf(v) as the reference's x86-64 build computes it (builtins.c:257-258): cvtss2si into a 64-bit long -- NaN and
 // |v| >= 2^63 give 0x8000000000000000 -- of which the cast keeps the low 32 bits.  So a NaN coordinate reads column / row 0
 // (not "out of range" as the 32-bit conversions of the drawable samplers make it), and so do 2^32, 2^33 ...
-MM_DEV int mm_lrintf_to_int(float v) { return fabsf(v) < 9223372036854775808.0f ? (int)__float2ll_rn(v) : 0; }
+MM_DEV int mm_lrintf_to_int(float v) {
+    if (fabsf(v) < 2147483648.0f) return __float2int_rn(v);  // the usual case: the 64-bit result fits its low word
+    return fabsf(v) < 9223372036854775808.0f ? (int)__float2ll_rn(v) : 0;
+}
 // get_floatmap_pixel, builtins.c:249-265: nearest via lrintf (round half even)
 MM_DEV mm_tup<4> mm_floatmap_pixel(const mm_image &img, float x, float y) {
     mm_tup<4> t;
