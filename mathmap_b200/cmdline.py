@@ -74,7 +74,7 @@ def main(argv=None):
         return 1
     if a.bench_no_backend or a.bench_only_compile:
         if not a.bench_no_backend:
-            module.compile_check(a.intersampling, not a.fast_math)
+            module.compile_check(a.intersampling, not a.fast_math, a.fast_compile)
         print("compiled %s in %.3f s" % (module.name, time.perf_counter() - t0), file=sys.stderr)
         return 0
 
