@@ -571,9 +571,20 @@ def main():
     except (OSError, ValueError):
         pass
     if world > 1:
-        # stdout carries the one JSON line: NCCL's own banner ("NCCL version ..." at NCCL_DEBUG=VERSION / WARN) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=ctx.dev)
+        # stdout carries the one JSON line: while the communicator comes up, file descriptor 1 points at stderr, so that NCCL's
+        # own banner ("NCCL version ..." at NCCL_DEBUG=VERSION / WARN, written by the C library) does not land in front of it
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=ctx.dev)
+            probe = torch.zeros(1, device=ctx.dev)
+            dist.all_reduce(probe)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
     head_name = args.workload or HEADLINE
