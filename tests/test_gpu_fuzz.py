@@ -12,12 +12,12 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 @pytest.mark.gpu
 def test_random_compositions_match_oracle():
     import fuzz_compositions
-    cases, failures = fuzz_compositions.run(2024, 30)
-    assert cases == 30 and not failures, failures
+    cases, failures = fuzz_compositions.run(2024, 24)
+    assert cases == 24 and not failures, failures
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,count,only,settings", [(7, 50, "", False), (8, 12, "Droste", False), (31, 60, "", True)])
+@pytest.mark.parametrize("seed,count,only,settings", [(7, 40, "", False), (8, 12, "Droste", False), (31, 48, "", True)])
 def test_random_arguments_match_oracle(seed, count, only, settings):
     """settings: also random edge behaviour and colours, supersampling, bytes per pixel, one-pixel-wide to several-tiles-wide
     frames (NaN coordinates, x86 conversions, the samplers' general paths)."""
