@@ -168,3 +168,130 @@ def test_oracle_matches_hand_evaluation_mandelbrot(size, n):
     got = OracleFilter(m.ir).render(W, H, {"num_iterations": n}, t=0.0)
     want = mandelbrot(W, H, n)
     assert np.array_equal(got, want), "%d pixels differ" % int((np.abs(got.astype(int) - want.astype(int)).max(axis=2) > 0).sum())
+
+
+# ---- edge behaviours and supersampling by hand (builtins.c:41-131, mathmap_common.c:874-936) --------------------------------
+def apply_edge(ix, iy, w, h, mode_x, mode_y):
+    """apply_edge_behaviour on int64 arrays of in-range-of-int32 values (finite coordinates only here)."""
+    ix, iy = ix.copy(), iy.copy()
+
+    def crem(a, b):  # C remainder: sign of the dividend
+        return np.sign(a) * (np.abs(a) % b)
+
+    if mode_x == 1:
+        ix = np.where(ix < 0, crem(ix, w) + w, np.where(ix >= w, ix % w, ix))
+    elif mode_x == 2:
+        ix = np.where(ix < 0, crem(-ix, w), np.where(ix >= w, (w - 1) - (ix % w), ix))
+    elif mode_x == 3:
+        flip = (ix < 0) | (ix >= w)
+        ix = np.where(ix < 0, crem(-ix, w), np.where(ix >= w, (w - 1) - (ix % w), ix))
+        iy = np.where(flip, (h - 1) - iy, iy)
+    if mode_y == 1:
+        iy = np.where(iy < 0, crem(iy, h) + h, np.where(iy >= h, iy % h, iy))
+    elif mode_y == 2:
+        iy = np.where(iy < 0, crem(-iy, h), np.where(iy >= h, (h - 1) - (iy % h), iy))
+    elif mode_y == 3:
+        flip = (iy < 0) | (iy >= h)
+        iy = np.where(iy < 0, crem(-iy, h), np.where(iy >= h, (h - 1) - (iy % h), iy))
+        ix = np.where(flip, (w - 1) - ix, ix)
+    return ix, iy
+
+
+def sample_edges(img, x, y, bilinear, modes, colors, supersampling=False):
+    """origVal with edge behaviours and edge colours (packed R<<24|G<<16|B<<8|A; x is tested first, builtins.c:121-131);
+    under supersampling the nearest sampler does not add 0.5 (builtins.c:155-159)."""
+    h, w = img.shape[:2]
+    m = max(w, h)
+    x = (x * F(F(m) / F(w))).astype(np.float32)
+    y = (y * F(F(m) / F(h))).astype(np.float32)
+    px = ((x + F(1.0)) * F((w - 1) / 2.0)).astype(np.float32)
+    py = (-((y - F(1.0)) * F((h - 1) / 2.0))).astype(np.float32)
+    texels = img.astype(np.float32)
+
+    def unpack(c):
+        return np.array([(c >> 24) & 255, (c >> 16) & 255, (c >> 8) & 255, c & 255], dtype=np.float32)
+
+    def texel(ix, iy):
+        ix, iy = apply_edge(ix, iy, w, h, modes[0], modes[1])
+        out_x = (ix < 0) | (ix >= w)
+        out_y = (iy < 0) | (iy >= h)
+        v = texels[np.clip(iy, 0, h - 1), np.clip(ix, 0, w - 1)]
+        v = np.where(out_y[..., None], unpack(colors[1]), v)
+        return np.where(out_x[..., None], unpack(colors[0]), v)
+
+    if not bilinear:
+        if not supersampling:
+            px = (px.astype(np.float64) + 0.5).astype(np.float32)
+            py = (py.astype(np.float64) + 0.5).astype(np.float32)
+        q = texel(np.floor(px).astype(np.int64), np.floor(py).astype(np.int64))
+    else:
+        x1 = np.floor(px).astype(np.int64)
+        y1 = np.floor(py).astype(np.int64)
+        x2f = (px - x1.astype(np.float32)).astype(np.float32)
+        y2f = (py - y1.astype(np.float32)).astype(np.float32)
+        x1f = (F(1.0) - x2f).astype(np.float32)
+        y1f = (F(1.0) - y2f).astype(np.float32)
+        p1, p2, p3, p4 = (x1f * y1f)[..., None], (x1f * y2f)[..., None], (x2f * y1f)[..., None], (x2f * y2f)[..., None]
+        c1, c2, c3, c4 = texel(x1, y1), texel(x1, y1 + 1), texel(x1 + 1, y1), texel(x1 + 1, y1 + 1)
+        s = (((c1 * p1).astype(np.float32) + (c2 * p2).astype(np.float32)).astype(np.float32) + (c3 * p3).astype(np.float32)).astype(np.float32)
+        s = (s + (c4 * p4).astype(np.float32)).astype(np.float32)
+        q = np.rint(s)
+    return (q.astype(np.float64) / 255.0).astype(np.float32)
+
+
+def coords_of(cols, rows, W, H, off):
+    """CALC_VIRTUAL_X/Y (opmacros.h:156-157) for column / row index arrays and a sampling offset, times the filter's X, Y"""
+    xu = ((cols.astype(np.float64) - (W - 1) / 2.0 + off) / ((W - 1) / 2.0)).astype(np.float32)
+    yu = ((-rows.astype(np.float64) + (H - 1) / 2.0 - off) / ((H - 1) / 2.0)).astype(np.float32)
+    m = max(W, H)
+    x = (xu * F(F(W) / F(m)))[None, :].repeat(len(rows), 0)
+    y = (yu * F(F(H) / F(m)))[:, None].repeat(len(cols), 1)
+    return x.astype(np.float32), y.astype(np.float32)
+
+
+@pytest.mark.parametrize("bilinear", [False, True], ids=["nearest", "bilinear"])
+@pytest.mark.parametrize("modes", [(1, 1), (2, 2), (3, 3), (3, 1), (0, 2), (2, 0)])
+def test_oracle_edge_behaviours_match_hand_evaluation(modes, bilinear):
+    """Geometry/Zoom `in(xy * factor)` with factor 2.7: most samples fall outside and come back through wrap / reflect / rotate."""
+    W, H = 83, 61
+    img = synthetic_rgba(57, 44, seed=11)
+    colors = (0x11223344, 0xA5667788)
+    m = mb.Module(source=filter_source("examples/Geometry/Zoom.mm"))
+    got = OracleFilter(m.ir).render(W, H, {"in": img, "factor": 2.7}, t=0.0, antialiasing=bilinear, edge_behaviour=modes, edge_colors=colors)
+    x, y = coords_of(np.arange(W), np.arange(H), W, H, 0.0)
+    want = quantise(sample_edges(img, (x * F(2.7)).astype(np.float32), (y * F(2.7)).astype(np.float32), bilinear, modes, colors))
+    assert np.array_equal(got, want), "%d pixels differ" % int((np.abs(got.astype(int) - want.astype(int)).max(axis=2) > 0).sum())
+
+
+@pytest.mark.parametrize("bilinear", [False, True], ids=["nearest", "bilinear"])
+def test_oracle_supersampling_matches_hand_evaluation(bilinear):
+    """-o (mathmap_common.c:874-936): per row the short line and two lines of a slice one column wider sampled at (-0.5, -0.5),
+    combined (l1[c] + l1[c+1] + 2 l2[c] + l3[c] + l3[c+1]) / 6 in integers; the row below the last one is clamped away and l3
+    keeps the previous line there.  Twirl at t = 0.3, one band (one thread)."""
+    W, H, t = 47, 38, 0.3
+    img = synthetic_rgba(W, H, seed=3)
+    m = mb.Module(source=filter_source("examples/Distorts/Twirl.mm"))
+    got = OracleFilter(m.ir).render(W, H, {"in": img}, t=t, antialiasing=bilinear, supersampling=True)
+
+    def twirl_at(x, y):
+        r = libm(np.hypot, x, y)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            a = libm(np.arccos, (x / r).astype(np.float32))
+        a = np.where(y < 0, (F(2 * math.pi) - a).astype(np.float32), a)
+        a = np.where(r == 0, F(0.0), a).astype(np.float32)
+        e = ((r / F(math.sqrt(2.0))).astype(np.float32) - F(1.0)).astype(np.float32)
+        e = (((e * F(F(t) - F(0.5))).astype(np.float32) * F(4.0)).astype(np.float32) * F(math.pi)).astype(np.float32)
+        a2 = (a + e).astype(np.float32)
+        r2 = (r + F(0.0)).astype(np.float32)
+        sx = (libm(np.cos, a2) * r2).astype(np.float32)
+        sy = (libm(np.sin, a2) * r2).astype(np.float32)
+        return quantise(sample_edges(img, sx, sy, bilinear, (0, 0), (0, 0), supersampling=True)).astype(np.int64)
+
+    short = twirl_at(*coords_of(np.arange(W), np.arange(H), W, H, 0.0))
+    longs = twirl_at(*coords_of(np.arange(W + 1), np.arange(H), W, H, -0.5))  # rows 0 .. H-1 of the wider slice; row H is clamped away
+    want = np.empty((H, W, 4), np.uint8)
+    for row in range(H):
+        l1 = longs[row]
+        l3 = longs[row + 1] if row + 1 < H else longs[row]
+        want[row] = ((l1[:-1] + l1[1:] + 2 * short[row] + l3[:-1] + l3[1:]) // 6).astype(np.uint8)
+    assert np.array_equal(got, want), "%d pixels differ" % int((np.abs(got.astype(int) - want.astype(int)).max(axis=2) > 0).sum())
