@@ -295,3 +295,80 @@ def test_oracle_supersampling_matches_hand_evaluation(bilinear):
         l3 = longs[row + 1] if row + 1 < H else longs[row]
         want[row] = ((l1[:-1] + l1[1:] + 2 * short[row] + l3[:-1] + l3[1:]) // 6).astype(np.uint8)
     assert np.array_equal(got, want), "%d pixels differ" % int((np.abs(got.astype(int) - want.astype(int)).max(axis=2) > 0).sum())
+
+
+# ---- the Gaussian blur's recursive filter by hand (native-filters/gauss.c:37-262) -------------------------------------------
+def iir_constants(std_dev):
+    """find_iir_constants (gauss.c:37-115) in Python doubles (math.* is the C library); std_dev is a float promoted to double."""
+    sd = float(np.float32(std_dev))
+    div = math.sqrt(2 * math.pi) * sd
+    x0, x1, x2, x3 = -1.783 / sd, -1.723 / sd, 0.6318 / sd, 1.997 / sd
+    x4, x5, x6, x7 = 1.6803 / div, 3.735 / div, -0.6803 / div, -0.2598 / div
+    e, s, c = math.exp, math.sin, math.cos
+    n_p = [x4 + x6,
+           (e(x1) * (x7 * s(x3) - (x6 + 2 * x4) * c(x3)) + e(x0) * (x5 * s(x2) - (2 * x6 + x4) * c(x2))),
+           (2 * e(x0 + x1) * ((x4 + x6) * c(x3) * c(x2) - x5 * c(x3) * s(x2) - x7 * c(x2) * s(x3)) + x6 * e(2 * x0) + x4 * e(2 * x1)),
+           (e(x1 + 2 * x0) * (x7 * s(x3) - x6 * c(x3)) + e(x0 + 2 * x1) * (x5 * s(x2) - x4 * c(x2))),
+           0.0]
+    d_p = [0.0,
+           -2 * e(x1) * c(x3) - 2 * e(x0) * c(x2),
+           4 * c(x3) * c(x2) * e(x0 + x1) + e(2 * x1) + e(2 * x0),
+           -2 * c(x2) * e(x0 + 2 * x1) - 2 * c(x3) * e(x1 + 2 * x0),
+           e(2 * x0 + 2 * x1)]
+    n_m = [0.0] + [n_p[i] - d_p[i] * n_p[0] for i in range(1, 5)]
+    sum_n_p = sum_n_m = sum_d = 0.0
+    for i in range(5):
+        sum_n_p += n_p[i]
+        sum_n_m += n_m[i]
+        sum_d += d_p[i]
+    a, b = sum_n_p / (1.0 + sum_d), sum_n_m / (1.0 + sum_d)
+    return n_p, n_m, d_p, [d * a for d in d_p], [d * b for d in d_p]
+
+
+def iir_lines(lines, std_dev):
+    """One pass of gauss_iir over `lines` [count, n] float32 (gauss.c:160-196): causal and anticausal 4th-order recursions with
+    double accumulators, every product and sum rounded on its own, in the reference's order of terms; float(vp + vm)."""
+    n_p, n_m, d_p, bd_p, bd_m = iir_constants(std_dev)
+    d_m = d_p
+    cnt, n = lines.shape
+    s = lines.astype(np.float64)
+    vp = np.zeros((cnt, n))
+    vm = np.zeros((cnt, n))
+    init_p, init_m = s[:, 0], s[:, n - 1]
+    for k in range(n):
+        terms = min(k, 4)
+        acc_p = np.zeros(cnt)
+        acc_m = np.zeros(cnt)
+        kp, km = k, n - 1 - k
+        for i in range(terms + 1):
+            prev_p = acc_p if i == 0 else vp[:, kp - i]
+            prev_m = acc_m if i == 0 else vm[:, km + i]
+            acc_p = acc_p + (n_p[i] * s[:, kp - i] - d_p[i] * prev_p)
+            acc_m = acc_m + (n_m[i] * s[:, km + i] - d_m[i] * prev_m)
+        for j in range(terms + 1, 5):
+            acc_p = acc_p + (n_p[j] - bd_p[j]) * init_p
+            acc_m = acc_m + (n_m[j] - bd_m[j]) * init_m
+        vp[:, kp] = acc_p
+        vm[:, km] = acc_m
+    return (vp + vm).astype(np.float32)
+
+
+@pytest.mark.parametrize("w,h,sh,sv", [(37, 23, 2.5, 1.7), (16, 41, 0.8, 6.0), (5, 3, 1.0, 1.0), (64, 9, 12.0, 0.6)])
+def test_oracle_gaussian_iir_matches_hand_evaluation(w, h, sh, sv):
+    """The oracle's gauss.c restatement (what the CUDA blur is compared with, raw float bits) against a numpy evaluation written
+    from the reference's source: columns first, then rows, per channel; equal bits."""
+    import ctypes
+    rng = np.random.default_rng(w * 100 + h)
+    data = rng.random((h, w, 4), dtype=np.float32)
+    data[rng.random((h, w)) < 0.25] = 0.0
+    got = np.ascontiguousarray(data.copy())
+    olib = OracleFilter(mb.Module(source="filter f () rgba:[1,0,0,1] end").ir).lib
+    olib.mmo_gaussian_blur_floats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]
+    olib.mmo_gaussian_blur_floats.restype = None
+    olib.mmo_gaussian_blur_floats(got.ctypes.data, w, h, sh, sv)
+    want = data.copy()
+    for ch in range(4):
+        want[:, :, ch] = iir_lines(np.ascontiguousarray(want[:, :, ch].T), sv).T  # the vertical pass first (gauss.c:155)
+    for ch in range(4):
+        want[:, :, ch] = iir_lines(np.ascontiguousarray(want[:, :, ch]), sh)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "max abs difference %g" % np.abs(got - want).max()
