@@ -372,3 +372,36 @@ def test_oracle_gaussian_iir_matches_hand_evaluation(w, h, sh, sv):
     for ch in range(4):
         want[:, :, ch] = iir_lines(np.ascontiguousarray(want[:, :, ch]), sh)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "max abs difference %g" % np.abs(got - want).max()
+
+
+# ---- output formats by hand (new_template.c.in:270-293) ---------------------------------------------------------------------
+@pytest.mark.parametrize("bpp", [1, 2, 3])
+def test_oracle_output_formats_match_hand_evaluation(bpp):
+    """1 and 2 bytes per pixel store (R * 0.299 + G * 0.587 + B * 0.114) * 255.0 of the clamped channels, computed in double
+    and truncated; 2 and 4 carry alpha in the last byte; 3 is RGB.  Twirl at t = 0.7 on a non-square frame, bilinear."""
+    W, H, t = 90, 61, 0.7
+    img = synthetic_rgba(W, H, seed=21)
+    m = mb.Module(source=filter_source("examples/Distorts/Twirl.mm"))
+    got = OracleFilter(m.ir).render(W, H, {"in": img}, t=t, antialiasing=True, bpp=bpp)
+    x, y, _, _ = virtual_coords(W, H)
+    r = libm(np.hypot, x, y)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a = libm(np.arccos, (x / r).astype(np.float32))
+    a = np.where(y < 0, (F(2 * math.pi) - a).astype(np.float32), a)
+    a = np.where(r == 0, F(0.0), a).astype(np.float32)
+    e = ((r / F(math.sqrt(2.0))).astype(np.float32) - F(1.0)).astype(np.float32)
+    e = (((e * F(F(t) - F(0.5))).astype(np.float32) * F(4.0)).astype(np.float32) * F(math.pi)).astype(np.float32)
+    a2 = (a + e).astype(np.float32)
+    tup = sample(img, (libm(np.cos, a2) * (r + F(0.0)).astype(np.float32)).astype(np.float32),
+                 (libm(np.sin, a2) * (r + F(0.0)).astype(np.float32)).astype(np.float32), True)
+    c = np.where(1.0 < tup, F(1.0), tup)
+    c = np.where(0.0 < c, c, F(0.0)).astype(np.float64)  # CLAMP01, then promoted to double by the double literals
+    gray = np.floor((c[..., 0] * 0.299 + c[..., 1] * 0.587 + c[..., 2] * 0.114) * 255.0).astype(np.uint8)
+    alpha = np.floor(c[..., 3] * 255.0).astype(np.uint8)
+    if bpp == 1:
+        want = gray[..., None]
+    elif bpp == 2:
+        want = np.stack([gray, alpha], axis=-1)
+    else:
+        want = np.floor(c[..., :3] * 255.0).astype(np.uint8)
+    assert np.array_equal(got, want), "%d pixels differ" % int((np.abs(got.astype(int) - want.astype(int)).max(axis=2) > 0).sum())
