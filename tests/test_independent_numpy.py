@@ -405,3 +405,79 @@ def test_oracle_output_formats_match_hand_evaluation(bpp):
     else:
         want = np.floor(c[..., :3] * 255.0).astype(np.uint8)
     assert np.array_equal(got, want), "%d pixels differ" % int((np.abs(got.astype(int) - want.astype(int)).max(axis=2) > 0).sum())
+
+
+# ---- coordinate systems by hand (mathmap_common.c:59-72, compiler.c:1710-1773, 2311-2420) -----------------------------------
+def sample_edges_factors(img, x, y, fx, fy, bilinear):
+    """origVal with the resize factors as arguments (None: a stretched image, no factors); edge colour (0, 0, 0, 0)"""
+    h, w = img.shape[:2]
+    if fx is not None:
+        x = (x * fx).astype(np.float32)
+        y = (y * fy).astype(np.float32)
+    px = ((x + F(1.0)) * F((w - 1) / 2.0)).astype(np.float32)
+    py = (-((y - F(1.0)) * F((h - 1) / 2.0))).astype(np.float32)
+    texels = img.astype(np.float32)
+
+    def texel(ix, iy):
+        inside = (ix >= 0) & (ix < w) & (iy >= 0) & (iy < h)
+        v = texels[np.clip(iy, 0, h - 1), np.clip(ix, 0, w - 1)]
+        return np.where(inside[..., None], v, F(0.0))
+
+    if not bilinear:
+        q = texel(np.floor((px.astype(np.float64) + 0.5).astype(np.float32)).astype(np.int64),
+                  np.floor((py.astype(np.float64) + 0.5).astype(np.float32)).astype(np.int64))
+    else:
+        x1 = np.floor(px).astype(np.int64)
+        y1 = np.floor(py).astype(np.int64)
+        x2f = (px - x1.astype(np.float32)).astype(np.float32)
+        y2f = (py - y1.astype(np.float32)).astype(np.float32)
+        x1f = (F(1.0) - x2f).astype(np.float32)
+        y1f = (F(1.0) - y2f).astype(np.float32)
+        p1, p2, p3, p4 = (x1f * y1f)[..., None], (x1f * y2f)[..., None], (x2f * y1f)[..., None], (x2f * y2f)[..., None]
+        c1, c2, c3, c4 = texel(x1, y1), texel(x1, y1 + 1), texel(x1 + 1, y1), texel(x1 + 1, y1 + 1)
+        s = (((c1 * p1).astype(np.float32) + (c2 * p2).astype(np.float32)).astype(np.float32) + (c3 * p3).astype(np.float32)).astype(np.float32)
+        s = (s + (c4 * p4).astype(np.float32)).astype(np.float32)
+        q = np.rint(s)
+    return (q.astype(np.float64) / 255.0).astype(np.float32)
+
+
+def unit_coords(W, H):
+    cols = np.arange(W, dtype=np.float64)
+    rows = np.arange(H, dtype=np.float64)
+    xu = ((cols - (W - 1) / 2.0) / ((W - 1) / 2.0)).astype(np.float32)
+    yu = ((-rows + (H - 1) / 2.0) / ((H - 1) / 2.0)).astype(np.float32)
+    return xu[None, :].repeat(H, 0), yu[:, None].repeat(W, 1)
+
+
+COORDINATE_FILTERS = {
+    # stretched filter: X = Y = 1 (W = H = 2); stretched image: no resize factors
+    "stretched": ("stretched filter s (stretched image in)\n  in(xy * 0.8 + xy:[0.1, -0.05] + xy:[W, H] * 0.01)\nend\n",
+                  lambda xu, yu, W, H, w, h: ((((xu * F(1.0)).astype(np.float32) * F(0.8)).astype(np.float32) + F(0.1)).astype(np.float32) + (F(2.0) * F(0.01)),
+                                              (((yu * F(1.0)).astype(np.float32) * F(0.8)).astype(np.float32) + F(-0.05)).astype(np.float32) + (F(2.0) * F(0.01)),
+                                              None, None)),
+    # pixel filter: X = (W - 1) / 2, Y = (H - 1) / 2 in pixels; pixel image: factors 2 / w, 2 / h
+    "pixel": ("pixel filter p (pixel image in)\n  in(xy + xy:[3.5, -2.25])\nend\n",
+              lambda xu, yu, W, H, w, h: (((xu * (F(W - 1) / F(2))).astype(np.float32) + F(3.5)).astype(np.float32),
+                                          ((yu * (F(H - 1) / F(2))).astype(np.float32) + F(-2.25)).astype(np.float32),
+                                          F(2) / F(w), F(2) / F(h))),
+    # default filter (unit, square: X = W / max, Y = H / max) sampling a pixel image
+    "default_on_pixel_image": ("filter m (pixel image in)\n  in(xy * 20)\nend\n",
+                               lambda xu, yu, W, H, w, h: (((xu * (F(W) / F(max(W, H)))).astype(np.float32) * F(20)).astype(np.float32),
+                                                           ((yu * (F(H) / F(max(W, H)))).astype(np.float32) * F(20)).astype(np.float32),
+                                                           F(2) / F(w), F(2) / F(h))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(COORDINATE_FILTERS))
+@pytest.mark.parametrize("bilinear", [False, True], ids=["nearest", "bilinear"])
+def test_oracle_coordinate_systems_match_hand_evaluation(name, bilinear):
+    src, coords = COORDINATE_FILTERS[name]
+    W, H, w, h = 71, 40, 53, 64
+    img = synthetic_rgba(w, h, seed=17)
+    m = mb.Module(source=src)
+    got = OracleFilter(m.ir).render(W, H, {"in": img}, t=0.0, antialiasing=bilinear)
+    xu, yu = unit_coords(W, H)
+    sx, sy, fx, fy = coords(xu, yu, W, H, w, h)
+    want = quantise(sample_edges_factors(img, np.asarray(sx, np.float32), np.asarray(sy, np.float32), fx, fy, bilinear))
+    diff = np.abs(got.astype(int) - want.astype(int)).max(axis=2)
+    assert np.array_equal(got, want), "%d pixels differ, max %d" % (int((diff > 0).sum()), int(diff.max()))
