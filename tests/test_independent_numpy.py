@@ -481,3 +481,27 @@ def test_oracle_coordinate_systems_match_hand_evaluation(name, bilinear):
     want = quantise(sample_edges_factors(img, np.asarray(sx, np.float32), np.asarray(sy, np.float32), fx, fy, bilinear))
     diff = np.abs(got.astype(int) - want.astype(int)).max(axis=2)
     assert np.array_equal(got, want), "%d pixels differ, max %d" % (int((diff > 0).sum()), int(diff.max()))
+
+
+# ---- the builtins' guards by hand (builtins.lisp:635-669, 804-817, 848-857, 873-876) ----------------------------------------
+def test_oracle_builtin_guards_match_hand_evaluation():
+    """x / 0 = 0, x % 0 = 0, asin outside [-1, 1] = 0, log(x <= 0) = 0; `%` is fmod in double; floor() is an int."""
+    src = ("filter g ()\n  k = floor(y * 3);\n"
+           "  rgba:[x / k / 8 + 0.5, asin(x * 2) / 3 + 0.5, log(x) / 6 + 0.5, (x * 4) % k / 8 + 0.5]\nend\n")
+    W, H = 97, 64
+    m = mb.Module(source=src)
+    got = OracleFilter(m.ir).render(W, H, {}, t=0.0)
+    x, y, _, _ = virtual_coords(W, H)
+    k = np.floor((y * F(3)).astype(np.float32)).astype(np.int32).astype(np.float32)  # int, converted back where a float is needed
+    with np.errstate(all="ignore"):
+        c0 = np.where(k == 0, F(0.0), (x / k).astype(np.float32))
+        x2 = (x * F(2)).astype(np.float32)
+        c1 = np.where((x2 < -1) | (x2 > 1), F(0.0), libm(np.arcsin, x2))
+        c2 = np.where(x <= 0, F(0.0), libm(np.log, x))
+        x4 = (x * F(4)).astype(np.float32)
+        c3 = np.where(k == 0, F(0.0), np.fmod(x4.astype(np.float64), k.astype(np.float64)).astype(np.float32))
+    ch = [((c0 / F(8)).astype(np.float32) + F(0.5)).astype(np.float32), ((c1 / F(3)).astype(np.float32) + F(0.5)).astype(np.float32),
+          ((c2 / F(6)).astype(np.float32) + F(0.5)).astype(np.float32), ((c3 / F(8)).astype(np.float32) + F(0.5)).astype(np.float32)]
+    want = quantise(np.stack(ch, axis=-1).astype(np.float32))
+    diff = np.abs(got.astype(int) - want.astype(int)).max(axis=2)
+    assert np.array_equal(got, want), "%d pixels differ, max %d" % (int((diff > 0).sum()), int(diff.max()))
