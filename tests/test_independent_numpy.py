@@ -505,3 +505,50 @@ def test_oracle_builtin_guards_match_hand_evaluation():
     want = quantise(np.stack(ch, axis=-1).astype(np.float32))
     diff = np.abs(got.astype(int) - want.astype(int)).max(axis=2)
     assert np.array_equal(got, want), "%d pixels differ, max %d" % (int((diff > 0).sum()), int(diff.max()))
+
+
+# ---- vector, matrix and interpolation builtins by hand (builtins.lisp:671-735, 1026-1090, 1173-1228) ------------------------
+def test_oracle_vector_builtins_match_hand_evaluation():
+    """crossp, normalize, dotp, det (2x2, 3x3), gray, pmod, clamp, lerp, scale, sign, inintv: every product and sum a float op,
+    sums and products of several terms taken left to right."""
+    src = ("filter b (image in)\n  p = in(xy);\n  v = v3:[x, y, 0.5];\n  w = v3:[0.2, x * y, 1];\n  c = crossp(v, w);\n  n = normalize(v);\n"
+           "  d3 = det(m3x3:[x, 0.3, y, 0.1, y, 0.2, 0.7, 0.4, x]);\n  d2 = det(m2x2:[x, y, 0.5, 0.25]);\n  g = gray(p);\n"
+           "  rgba:[scale(dotp(c, n), -1, 1, 0, 1), lerp(g, pmod(x * 3, 0.7), clamp(d3, -0.2, 0.6)), sign(d2) * 0.25 + 0.5, inintv(g, 0.3, 0.6) * 0.5 + 0.25]\nend\n")
+    W, H = 101, 75
+    img = synthetic_rgba(W, H, seed=9)
+    m = mb.Module(source=src)
+    got = OracleFilter(m.ir).render(W, H, {"in": img}, t=0.0)
+    x, y, _, _ = virtual_coords(W, H)
+    f = lambda v: np.asarray(v, dtype=np.float32)
+    mul = lambda u, v: (f(u) * f(v)).astype(np.float32)
+    add = lambda u, v: (f(u) + f(v)).astype(np.float32)
+    sub = lambda u, v: (f(u) - f(v)).astype(np.float32)
+    div = lambda u, v: (f(u) / f(v)).astype(np.float32)
+    p = sample(img, x, y, False)
+    half = np.full_like(x, 0.5)
+    one = np.ones_like(x)
+    xy_ = mul(x, y)
+    v = [x, y, half]
+    w = [np.full_like(x, F(0.2)), xy_, one]
+    c = [sub(mul(v[1], w[2]), mul(v[2], w[1])), sub(mul(v[2], w[0]), mul(v[0], w[2])), sub(mul(v[0], w[1]), mul(v[1], w[0]))]
+    l = add(add(mul(x, x), mul(y, y)), mul(half, half))
+    root = libm(np.sqrt, l)
+    n = [np.where(l == 0, F(0), div(q, root)) for q in v]
+    dot = add(add(mul(c[0], n[0]), mul(c[1], n[1])), mul(c[2], n[2]))
+    ch0 = add(mul(div(sub(dot, F(-1)), sub(F(1), F(-1))), sub(F(1), F(0))), F(0))
+    a = [x, np.full_like(x, F(0.3)), y, np.full_like(x, F(0.1)), y, np.full_like(x, F(0.2)), np.full_like(x, F(0.7)), np.full_like(x, F(0.4)), x]
+    t3 = lambda i, j, k: mul(mul(a[i], a[j]), a[k])
+    d3 = sub(add(add(t3(0, 4, 8), t3(1, 5, 6)), t3(2, 3, 7)), add(add(t3(2, 4, 6), t3(0, 5, 7)), t3(1, 3, 8)))
+    d2 = sub(mul(x, F(0.25)), mul(y, F(0.5)))
+    g = add(add(mul(F(0.299), p[..., 0]), mul(F(0.587), p[..., 1])), mul(F(0.114), p[..., 2]))
+    x3 = mul(x, F(3))
+    mod = np.fmod(x3.astype(np.float64), np.float64(F(0.7))).astype(np.float32)
+    pm = np.where(x3 < 0, add(mod, F(0.7)), mod)
+    cl = np.where(d3 < F(-0.2), F(-0.2), np.where(F(0.6) < d3, F(0.6), d3)).astype(np.float32)
+    ch1 = add(mul(sub(F(1), g), pm), mul(g, cl))
+    sg = np.where(d2 < 0, F(-1), np.where(0 < d2, F(1), F(0))).astype(np.float32)
+    ch2 = add(mul(sg, F(0.25)), F(0.5))
+    ch3 = add(mul(np.where((F(0.3) <= g) & (g <= F(0.6)), F(1), F(0)).astype(np.float32), F(0.5)), F(0.25))
+    want = quantise(np.stack([ch0, ch1, ch2, ch3], axis=-1).astype(np.float32))
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert np.array_equal(got, want), "pixels differing per channel %r, max %d" % ((diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
