@@ -552,3 +552,55 @@ def test_oracle_vector_builtins_match_hand_evaluation():
     want = quantise(np.stack([ch0, ch1, ch2, ch3], axis=-1).astype(np.float32))
     diff = np.abs(got.astype(int) - want.astype(int))
     assert np.array_equal(got, want), "pixels differing per channel %r, max %d" % ((diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
+
+
+# ---- colour conversions by hand (builtins.lisp:1251-1322) -------------------------------------------------------------------
+def test_oracle_hsv_conversions_match_hand_evaluation():
+    """toHSVA, a hue rotation and desaturation depending on t, toRGBA: max / min with int constants, `= r max` branch order,
+    h / 6.0, floor(h * 6) as an int and the six sectors."""
+    src = "filter c (image in)\n  h = toHSVA(in(xy));\n  toRGBA(hsva:[h[0] + t, h[1] * 0.75, h[2], h[3]])\nend\n"
+    W, H, t = 88, 66, 0.37
+    img = synthetic_rgba(W, H, seed=13)
+    img[:8] = img[:8, :, :1]  # grey rows: delta = 0 (division guard) and s = 0
+    img[8:12] = 0             # black rows: max = 0
+    m = mb.Module(source=src)
+    got = OracleFilter(m.ir).render(W, H, {"in": img}, t=t)
+    x, y, _, _ = virtual_coords(W, H)
+    f = lambda v: np.asarray(v, dtype=np.float32)
+    mul = lambda u, v: (f(u) * f(v)).astype(np.float32)
+    add = lambda u, v: (f(u) + f(v)).astype(np.float32)
+    sub = lambda u, v: (f(u) - f(v)).astype(np.float32)
+    with np.errstate(all="ignore"):
+        div = lambda u, v: np.where(f(v) == 0, F(0), (f(u) / f(v))).astype(np.float32)  # the `/` builtin's guard
+        p = sample(img, x, y, False)
+        clamp01 = lambda v: np.maximum(F(0), np.minimum(F(1), v)).astype(np.float32)
+        r, g, b, al = clamp01(p[..., 0]), clamp01(p[..., 1]), clamp01(p[..., 2]), clamp01(p[..., 3])
+        mx = np.maximum(r, np.maximum(g, b))
+        mn = np.minimum(r, np.minimum(g, b))
+        delta = sub(mx, mn)
+        sat = div(delta, mx)
+        hh = np.where(r == mx, div(sub(g, b), delta), np.where(g == mx, add(F(2), div(sub(b, r), delta)), add(F(4), div(sub(r, g), delta))))
+        hh = div(hh, F(6.0))
+        hue = np.where(hh < 0, add(hh, F(1)), hh)
+        hue = np.where(mx == 0, F(0), hue).astype(np.float32)
+        sat = np.where(mx == 0, F(0), sat).astype(np.float32)
+        # the filter's own arithmetic
+        h2, s2, v2, a2 = add(hue, F(t)), mul(sat, F(0.75)), mx, al
+        # toRGBA
+        s = clamp01(s2)
+        v = clamp01(v2)
+        a_out = clamp01(a2)
+        hcl = np.maximum(F(0), h2).astype(np.float32)
+        h6 = np.where(F(1) <= hcl, F(0), mul(hcl, F(6))).astype(np.float32)
+        i = np.floor(h6).astype(np.int32)
+        fr = sub(h6, i.astype(np.float32))
+        pp = mul(v, sub(F(1), s))
+        qq = mul(v, sub(F(1), mul(s, fr)))
+        tt = mul(v, sub(F(1), mul(s, sub(F(1), fr))))
+        sel = lambda c0, c1, c2, c3, c4, c5: np.where(i == 0, c0, np.where(i == 1, c1, np.where(i == 2, c2, np.where(i == 3, c3, np.where(i == 4, c4, c5)))))
+        R = np.where(s == 0, v, sel(v, qq, pp, pp, tt, v))
+        G = np.where(s == 0, v, sel(tt, v, v, qq, pp, pp))
+        B = np.where(s == 0, v, sel(pp, pp, tt, v, v, qq))
+    want = quantise(np.stack([R, G, B, a_out], axis=-1).astype(np.float32))
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert np.array_equal(got, want), "pixels differing per channel %r, max %d" % ((diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
