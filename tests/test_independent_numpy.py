@@ -604,3 +604,25 @@ def test_oracle_hsv_conversions_match_hand_evaluation():
     want = quantise(np.stack([R, G, B, a_out], axis=-1).astype(np.float32))
     diff = np.abs(got.astype(int) - want.astype(int))
     assert np.array_equal(got, want), "pixels differing per channel %r, max %d" % ((diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
+
+
+# ---- curves and gradients by hand (opmacros.h:128, 192-194) -----------------------------------------------------------------
+def test_oracle_curve_and_gradient_lookup_match_hand_evaluation():
+    """values[(int)(CLAMP01(p) * 1023)]: a float product, truncated; gradient colours packed R<<24|G<<16|B<<8|A, channels / 255.0."""
+    src = "filter cg (curve c, gradient g)\n  v = c(x * 0.6 + 0.5);\n  g(v * 0.8 + y * 0.3)\nend\n"
+    W, H = 120, 90
+    curve = (np.sqrt(np.arange(1024, dtype=np.float64) / 1023.0)).astype(np.float32)
+    grad = np.random.RandomState(5).randint(0, 1 << 32, size=1024, dtype=np.uint64).astype(np.uint32)
+    m = mb.Module(source=src)
+    got = OracleFilter(m.ir).render(W, H, {"c": curve, "g": grad}, t=0.0)
+    x, y, _, _ = virtual_coords(W, H)
+    clamp01 = lambda v: np.where(0.0 < np.where(1.0 < v, F(1.0), v), np.where(1.0 < v, F(1.0), v), F(0.0)).astype(np.float32)
+    index = lambda v: (clamp01(v) * F(1023)).astype(np.float32).astype(np.int64)
+    p1 = ((x * F(0.6)).astype(np.float32) + F(0.5)).astype(np.float32)
+    v = curve[index(p1)]
+    p2 = ((v * F(0.8)).astype(np.float32) + (y * F(0.3)).astype(np.float32)).astype(np.float32)
+    col = grad[index(p2)].astype(np.uint64)
+    tup = np.stack([(col >> 24) & 255, (col >> 16) & 255, (col >> 8) & 255, col & 255], axis=-1).astype(np.float64)
+    want = quantise((tup / 255.0).astype(np.float32))
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert np.array_equal(got, want), "pixels differing per channel %r, max %d" % ((diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
