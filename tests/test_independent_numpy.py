@@ -626,3 +626,34 @@ def test_oracle_curve_and_gradient_lookup_match_hand_evaluation():
     want = quantise((tup / 255.0).astype(np.float32))
     diff = np.abs(got.astype(int) - want.astype(int))
     assert np.array_equal(got, want), "pixels differing per channel %r, max %d" % ((diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
+
+
+# ---- closures and filter calls by hand (opmacros.h:199-216, new_template.c.in:375-422) --------------------------------------
+def test_oracle_closures_and_filter_calls_match_hand_evaluation():
+    """A filter applied to an image is an image (closure): sampling it runs the filter's body at the sample's coordinates, the
+    result stays a float tuple (nothing is quantised in between); a call with explicit coordinates is the same evaluation.
+    The coordinates pass through two conversions on the way in: the closure is a unit-square image whose pixel size the
+    optimiser takes from its first image argument (compopt/simplify.c:28-45), so they are multiplied by max/w, max/h of THAT
+    image (compiler.c:2219, 1747-1760), and the callee then binds its x, y as argument * X, * Y (compiler.c:2406-2420).  All
+    goldens are square, where every one of these factors is 1: this non-square case is what pins them."""
+    src = ("filter inner (image in, float k: 0-2 (1))\n  in(xy * k)\nend\n\n"
+           "filter outer (image in)\n  half = inner(in, 0.5);\n  half(xy + xy:[0.1, 0]) * 0.5 + inner(in, 1.5, xy * 0.5) * 0.25\nend\n")
+    W, H, w, h = 93, 58, 70, 81
+    img = synthetic_rgba(w, h, seed=23)
+    m = mb.Module(source=src)
+    x, y, X, Y = virtual_coords(W, H)
+    mul = lambda u, v: (np.asarray(u, np.float32) * np.asarray(v, np.float32)).astype(np.float32)
+    add = lambda u, v: (np.asarray(u, np.float32) + np.asarray(v, np.float32)).astype(np.float32)
+    fx, fy = F(F(max(w, h)) / F(w)), F(F(max(w, h)) / F(h))
+
+    def through_inner(cx, cy, k, bilinear):
+        cx, cy = mul(mul(cx, fx), X), mul(mul(cy, fy), Y)
+        return sample(img, mul(cx, F(k)), mul(cy, F(k)), bilinear)
+
+    for bilinear in (False, True):
+        got = OracleFilter(m.ir).render(W, H, {"in": img}, t=0.0, antialiasing=bilinear)
+        first = through_inner(add(x, F(0.1)), add(y, F(0)), 0.5, bilinear)
+        second = through_inner(mul(x, F(0.5)), mul(y, F(0.5)), 1.5, bilinear)
+        want = quantise(add(mul(first, F(0.5)), mul(second, F(0.25))))
+        diff = np.abs(got.astype(int) - want.astype(int))
+        assert np.array_equal(got, want), "bilinear=%s: pixels differing per channel %r, max %d" % (bilinear, (diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
