@@ -657,3 +657,39 @@ def test_oracle_closures_and_filter_calls_match_hand_evaluation():
         want = quantise(add(mul(first, F(0.5)), mul(second, F(0.25))))
         diff = np.abs(got.astype(int) - want.astype(int))
         assert np.array_equal(got, want), "bilinear=%s: pixels differing per channel %r, max %d" % (bilinear, (diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
+
+
+# ---- render() of a closure by hand (builtins.c:249-345) ---------------------------------------------------------------------
+def test_oracle_render_of_a_closure_matches_hand_evaluation():
+    """render(closure): a floatmap of the render size, each pixel the closure evaluated at fx = ((float)x - bx) / ax (float
+    arithmetic, ax = bx = (W - 1) / 2, ay = -by) through ORIG_VAL with frame argument 0.0 -- so the callee's t is 0 whatever
+    the frame's t is; the lookup afterwards is get_floatmap_pixel's lrintf(ax * x + bx), without resize factors."""
+    src = ("filter inner (image in, float k: 0-2 (1))\n  in(xy * k + xy:[t, 0])\nend\n\n"
+           "filter outer (image in)\n  rr = render(inner(in, 0.8));\n  rr(xy * 0.9 + xy:[t * 0.1, 0])\nend\n")
+    W, H, w, h, t = 77, 52, 64, 90, 0.3
+    img = synthetic_rgba(w, h, seed=29)
+    m = mb.Module(source=src)
+    x, y, X, Y = virtual_coords(W, H)
+    mul = lambda u, v: (np.asarray(u, np.float32) * np.asarray(v, np.float32)).astype(np.float32)
+    add = lambda u, v: (np.asarray(u, np.float32) + np.asarray(v, np.float32)).astype(np.float32)
+    sub = lambda u, v: (np.asarray(u, np.float32) - np.asarray(v, np.float32)).astype(np.float32)
+    div = lambda u, v: (np.asarray(u, np.float32) / np.asarray(v, np.float32)).astype(np.float32)
+    ax = bx = F((W - 1) / 2.0)
+    by = F((H - 1) / 2.0)
+    ay = F(-by)
+    fx, fy = F(F(max(w, h)) / F(w)), F(F(max(w, h)) / F(h))
+    for bilinear in (False, True):
+        got = OracleFilter(m.ir).render(W, H, {"in": img}, t=t, antialiasing=bilinear)
+        gx = div(sub(np.arange(W, dtype=np.float32), bx), ax)[None, :].repeat(H, 0)
+        gy = div(sub(np.arange(H, dtype=np.float32), by), ay)[:, None].repeat(W, 1)
+        cx, cy = mul(mul(gx, fx), X), mul(mul(gy, fy), Y)          # the resize wrapper's factors, then the callee's x = arg * X
+        rendered = sample(img, add(mul(cx, F(0.8)), F(0.0)), add(mul(cy, F(0.8)), F(0)), bilinear)  # t is 0 inside the rendering
+        lx = add(mul(x, F(0.9)), mul(F(t), F(0.1)))
+        ly = add(mul(y, F(0.9)), F(0))
+        ix = np.rint(add(mul(ax, lx), bx)).astype(np.int64)
+        iy = np.rint(add(mul(ay, ly), by)).astype(np.int64)
+        inside = (ix >= 0) & (ix < W) & (iy >= 0) & (iy < H)
+        tup = np.where(inside[..., None], rendered[np.clip(iy, 0, H - 1), np.clip(ix, 0, W - 1)], F(0))
+        want = quantise(tup.astype(np.float32))
+        diff = np.abs(got.astype(int) - want.astype(int))
+        assert np.array_equal(got, want), "bilinear=%s: pixels differing per channel %r, max %d" % (bilinear, (diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
