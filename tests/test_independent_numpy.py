@@ -693,3 +693,38 @@ def test_oracle_render_of_a_closure_matches_hand_evaluation():
         want = quantise(tup.astype(np.float32))
         diff = np.abs(got.astype(int) - want.astype(int))
         assert np.array_equal(got, want), "bilinear=%s: pixels differing per channel %r, max %d" % (bilinear, (diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
+
+
+# ---- complex arithmetic by hand (builtins.lisp:485-496, 599-611, 880-886) ---------------------------------------------------
+def test_oracle_complex_arithmetic_matches_hand_evaluation():
+    """Complex product, quotient (with its all-zero guard; inner `/` is the raw float division), conjugate, magnitude (hypot in
+    double) -- Droste's building blocks, lowered to float ops in the order the builtins spell them."""
+    src = ("filter z ()\n  p = ri:[x * 2, y * 3];\n  q = ri:[floor(x * 3), floor(y * 2)];\n  m = p * q;\n  d = p / q;\n  c = conj(d) * 0.25;\n"
+           "  rgba:[m[0] / 16 + 0.5, m[1] / 16 + 0.5, c[0] + c[1] + 0.5, abs(p) / 4]\nend\n")
+    W, H = 110, 70
+    m = mb.Module(source=src)
+    got = OracleFilter(m.ir).render(W, H, {}, t=0.0)
+    x, y, _, _ = virtual_coords(W, H)
+    f = lambda v: np.asarray(v, dtype=np.float32)
+    mul = lambda u, v: (f(u) * f(v)).astype(np.float32)
+    add = lambda u, v: (f(u) + f(v)).astype(np.float32)
+    sub = lambda u, v: (f(u) - f(v)).astype(np.float32)
+    with np.errstate(all="ignore"):
+        rdiv = lambda u, v: (f(u) / f(v)).astype(np.float32)
+        gdiv = lambda u, v: np.where(f(v) == 0, F(0), rdiv(u, v)).astype(np.float32)  # the language-level `/`
+        p0, p1 = mul(x, F(2)), mul(y, F(3))
+        q0 = np.floor(mul(x, F(3))).astype(np.int32).astype(np.float32)
+        q1 = np.floor(mul(y, F(2))).astype(np.int32).astype(np.float32)
+        m0 = sub(mul(p0, q0), mul(p1, q1))
+        m1 = add(mul(p0, q1), mul(q0, p1))
+        cc = add(mul(q0, q0), mul(q1, q1))
+        d0 = rdiv(add(mul(p0, q0), mul(p1, q1)), cc)
+        d1 = rdiv(add(mul((-p0).astype(np.float32), q1), mul(q0, p1)), cc)
+        zero = (q0 == 0) & (q1 == 0)
+        d0 = np.where(zero, F(0), d0).astype(np.float32)
+        d1 = np.where(zero, F(0), d1).astype(np.float32)
+        c0, c1 = mul(d0, F(0.25)), mul((-d1).astype(np.float32), F(0.25))
+        ch = [add(gdiv(m0, F(16)), F(0.5)), add(gdiv(m1, F(16)), F(0.5)), add(add(c0, c1), F(0.5)), gdiv(libm(np.hypot, p0, p1), F(4))]
+    want = quantise(np.stack(ch, axis=-1).astype(np.float32))
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert np.array_equal(got, want), "pixels differing per channel %r, max %d" % ((diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
