@@ -728,3 +728,102 @@ def test_oracle_complex_arithmetic_matches_hand_evaluation():
     want = quantise(np.stack(ch, axis=-1).astype(np.float32))
     diff = np.abs(got.astype(int) - want.astype(int))
     assert np.array_equal(got, want), "pixels differing per channel %r, max %d" % ((diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
+
+
+# ---- the Gaussian blur's run-length FIR by hand (native-filters/gauss.c:264-633) --------------------------------------------
+def rle_curve(sigma):
+    """make_rle_curve: float curve and its running sums; note that `total` leaves the curve's last tap out."""
+    sigma = float(np.float32(sigma))
+    sigma2 = 2 * sigma * sigma
+    l = math.sqrt(-sigma2 * math.log(1.0 / 255.0))
+    n = int(math.ceil(l)) * 2
+    if n % 2 == 0:
+        n += 1
+    length = n // 2
+    curve = {0: F(1.0)}
+    for i in range(1, length + 1):
+        curve[i] = curve[-i] = F(math.exp(-(i * i) / sigma2))
+    sums = [F(0)]
+    for i in range(1, 2 * length + 1):
+        sums.append(F(curve[i - length - 1] + sums[i - 1]))
+    csum = {k - length: sums[k] for k in range(2 * length + 1)}
+    return curve, csum, length, F(csum[length] - csum[-length])
+
+
+def fir_line(line, sigma):
+    """One line through run_length_encode + do_encoded_lre / do_full_lre, in float32 scalars, in the reference's order."""
+    n = len(line)
+    curve, csum, length, total = rle_curve(sigma)
+    pix, rle = {}, {}
+    idx = n + length - 1
+    last, count, same = line[n - 1], 0, 0
+    for _ in range(length):                     # the 'end' border
+        count += 1
+        pix[idx], rle[idx] = last, count
+        idx -= 1
+    for k in range(n - 1, -1, -1):              # the real pixels, from the right
+        c = line[k]
+        if c == last:
+            count += 1
+            same += 1
+        else:
+            count, last = 1, c
+        pix[idx], rle[idx] = last, count
+        idx -= 1
+    for _ in range(length):                     # the start border
+        count += 1
+        pix[idx], rle[idx] = last, count
+        idx -= 1
+    out = np.empty(n, np.float32)
+    if same > (3 * n) // 4:
+        ctotal = int(total)                     # do_encoded_lre takes `int ctotal`
+        for col in range(n):
+            val = F(0.0)
+            pos = col - length
+            s1 = csum[-length]
+            nb = rle[pos]
+            i = -length + nb
+            while i <= length:
+                s2 = int(csum[i])               # `int s2 = csum[i]`
+                val = F(val + F(pix[pos] * F(F(s2) - s1)))
+                s1 = F(s2)
+                pos += nb
+                nb = rle[pos]
+                i += nb
+            val = F(val + F(pix[pos] * F(csum[length] - s1)))
+            out[col] = F(val / F(ctotal))
+    else:
+        for col in range(n):
+            val = F(F(0.0) + F(pix[col] * curve[0]))
+            for i in range(1, length + 1):
+                val = F(val + F(F(pix[col + i] + pix[col - i]) * curve[i]))
+            out[col] = F(val / total)
+    return out
+
+
+@pytest.mark.parametrize("w,h,sh,sv,runs", [(23, 17, 0.45, 0.3, False), (19, 26, 0.3, 3.0, False), (40, 12, 2.0, 0.4, True), (31, 9, 0.0, 0.45, False)])
+def test_oracle_gaussian_fir_matches_hand_evaluation(w, h, sh, sv, runs):
+    """Either sigma below half a pixel sends both axes through gauss_rle (gauss.c:659-662): per line a run-length encoding with
+    replicated borders, then the plain FIR -- or, when more than three quarters of the samples repeat their right neighbour, the
+    run-length variant with its int-truncated running sums and int total.  A sigma of 0 skips its pass.  Raw float bits."""
+    import ctypes
+    rng = np.random.default_rng(w * 100 + h)
+    data = rng.random((h, w, 4), dtype=np.float32)
+    if runs:
+        data[:, 3:] = data[:, 2:3]              # long runs along the rows: the encoded variant in the horizontal pass
+        data[:, :, 1] = np.float32(200.0)       # values above 1: the int truncations show
+    got = np.ascontiguousarray(data.copy())
+    olib = OracleFilter(mb.Module(source="filter f () rgba:[1,0,0,1] end").ir).lib
+    olib.mmo_gaussian_blur_floats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]
+    olib.mmo_gaussian_blur_floats.restype = None
+    olib.mmo_gaussian_blur_floats(got.ctypes.data, w, h, sh, sv)
+    want = data.copy()
+    if sv > 0.0:
+        for col in range(w):
+            for ch in range(4):
+                want[:, col, ch] = fir_line(want[:, col, ch].copy(), sv)
+    if sh > 0.0:
+        for row in range(h):
+            for ch in range(4):
+                want[row, :, ch] = fir_line(want[row, :, ch].copy(), sh)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "max abs difference %g" % np.abs(got - want).max()
