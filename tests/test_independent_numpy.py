@@ -827,3 +827,39 @@ def test_oracle_gaussian_fir_matches_hand_evaluation(w, h, sh, sv, runs):
             for ch in range(4):
                 want[row, :, ch] = fir_line(want[row, :, ch].copy(), sh)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "max abs difference %g" % np.abs(got - want).max()
+
+
+# ---- config 4 end to end by hand: Blur/Gaussian Blur.mm on a non-square frame (gauss.c:643-670, builtins.c:269-345) ----------
+@pytest.mark.parametrize("bilinear", [False, True], ids=["nearest", "bilinear"])
+def test_oracle_gaussian_blur_filter_matches_hand_evaluation(bilinear):
+    """The whole filter: sigmas from dev * maxdim / size (guarded `/`), the drawable resampled into a floatmap of the render size
+    with the NEAREST sampler whatever -i says (builtins.c:306) at fx = ((float)x - bx) / ax, sigma_px = |s * ax|, |s * ay|, the
+    recursive filter columns first, the lrintf lookup at the stretched filter's own coordinates, quantisation."""
+    W, H, w, h, dev = 75, 48, 60, 70, 0.05
+    img = synthetic_rgba(w, h, seed=31)
+    m = mb.Module(source=filter_source("examples/Blur/Gaussian Blur.mm"))
+    got = OracleFilter(m.ir).render(W, H, {"in": img, "dev": dev}, t=0.0, antialiasing=bilinear)
+    f = lambda v: np.asarray(v, dtype=np.float32)
+    maxdim = F(max(w, h))
+    hs = F(F(F(dev) * maxdim) / F(w))
+    vs = F(F(F(dev) * maxdim) / F(h))
+    ax = bx = F((W - 1) / 2.0)
+    by = F((H - 1) / 2.0)
+    ay = F(-by)
+    gx = ((np.arange(W, dtype=np.float32) - bx) / ax).astype(np.float32)[None, :].repeat(H, 0)
+    gy = ((np.arange(H, dtype=np.float32) - by) / ay).astype(np.float32)[:, None].repeat(W, 1)
+    fm = sample_edges_factors(img, gx, gy, None, None, False)              # stretched image: no factors; nearest
+    sigma_h, sigma_v = abs(F(hs * ax)), abs(F(vs * ay))
+    assert sigma_h >= 0.5 and sigma_v >= 0.5
+    for ch in range(4):
+        fm[:, :, ch] = iir_lines(np.ascontiguousarray(fm[:, :, ch].T), sigma_v).T
+    for ch in range(4):
+        fm[:, :, ch] = iir_lines(np.ascontiguousarray(fm[:, :, ch]), sigma_h)
+    xu, yu = unit_coords(W, H)                                             # a stretched filter's x, y are the unit coordinates
+    ix = np.rint((f(ax * xu) + bx).astype(np.float32)).astype(np.int64)
+    iy = np.rint((f(ay * yu) + by).astype(np.float32)).astype(np.int64)
+    inside = (ix >= 0) & (ix < W) & (iy >= 0) & (iy < H)
+    tup = np.where(inside[..., None], fm[np.clip(iy, 0, H - 1), np.clip(ix, 0, W - 1)], F(0))
+    want = quantise(tup.astype(np.float32))
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert np.array_equal(got, want), "pixels differing per channel %r, max %d" % ((diff > 0).sum(axis=(0, 1)).tolist(), int(diff.max()))
