@@ -57,10 +57,15 @@ WORKLOADS = {
                    desc="Render/Perlin Noise.mm -s 8192x8192 (5 octaves, libnoise in double)"),
 }
 HEADLINE = "mandelbrot"
-# Optimised IR per loop iteration: 20 MUL + 19 ADD (+ 6 NEG, which are operand sign modifiers in SASS, not instructions,
-# + 1 SQRT that the emitter removes exactly: sqrt(s) < 2 <=> s < 4 for correctly rounded sqrt).  No FMA credit:
-# --fmad=false is required for bit parity.  SURVEY.md section 8d counts 45 (with the NEGs); 39 is the instruction-level figure.
-MANDELBROT_FLOPS_PER_ITERATION = 39
+# Render/Mandelbrot.mm iterates a QUATERNION square: c*c + p, then |c| < 2.  Distinct float operations per iteration, which is
+# what the reference's arithmetic needs and what the kernel's loop executes: 10 products (the 16 of the quaternion product
+# hold 6 commutative pairs a*b / b*a; the 4 squares for |c| are the next iteration's a*a, b*b, c*c, d*d, carried in registers
+# by the loop-carried value pass, csrc/ir/passes.cpp) + 19 sums (12 + 4 for c*c + p, 3 for |c|^2); the 6 NEGs are operand
+# sign modifiers in SASS and the SQRT goes exactly (sqrt(s) < 2 <=> s < 4 for a correctly rounded sqrt).  No FMA credit:
+# --fmad=false is required for bit parity.  The loop is 33 SASS instructions: these 29 + counter, two compares, branch, so
+# an all-issue-slots-busy kernel reaches 29/33 = 0.879 of this roofline.  (Rounds 1-2 counted the IR's 20 MUL + 19 ADD = 39,
+# of which the loop then executed 14 + 19 in 37 instructions; SURVEY.md section 8d's 45 includes the NEGs.)
+MANDELBROT_FLOPS_PER_ITERATION = 29
 # The blur's recursion (gauss.c:175-196): per step 9 DMUL + 4 DSUB + 5 DADD = 18 double operations, + 1 DADD for vp + vm per
 # output sample (half a DADD per sweep step); 2 passes x 2 sweeps x 4 channels steps per pixel.  No FMA (bit parity with the host).
 GAUSS_FP64_OPS_PER_PIXEL = 2 * 2 * 4 * 18.5
@@ -413,7 +418,7 @@ def measure(name, ctx, args, with_cpu):
         res["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                            "traffic": traffic,
                            "note": "non-FMA FP32 issue roofline: 148 SMs x 128 lanes x %.0f MHz (median SM clock under load); "
-                                   "39 flops (20 MUL + 19 ADD) per iteration x %d iterations per launch on this rank; output writes are %.1f GB/s of the %s %.0f GB/s HBM peak; "
+                                   "29 distinct float operations (10 MUL + 19 ADD) per iteration of the quaternion loop, 33 SASS instructions with the loop control (issue-slot ceiling 29/33 = 0.879) x %d iterations per launch on this rank; output writes are %.1f GB/s of the %s %.0f GB/s HBM peak; "
                                    "traffic = DRAM bytes per launch, %s (algorithmic: %.3e output bytes per rank)"
                                    % (sm_mhz, my_iters, my_rows * W * 4 / (kernel_ms / 1e3) / 1e9, hbm_src, hbm_peak, traffic_src, my_rows * W * 4)}
     else:

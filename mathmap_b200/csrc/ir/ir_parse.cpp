@@ -293,6 +293,7 @@ std::unique_ptr<mmb_module> load_ir_text(const std::string &text) {
             b.cvs[id] = c;
         }
         code->first = b.stmts(f[5], 1, nullptr);
+        carry_loop_values(mod, *code);
         propagate_types(*code);
         analyze_constants(*code);
         m->codes[fp->index] = std::move(code);

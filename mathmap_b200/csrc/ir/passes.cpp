@@ -12,6 +12,7 @@
 #include "passes.h"
 
 #include <cassert>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <set>
@@ -238,6 +239,100 @@ struct Optimizer {
                 changed |= cse_list(s->alt, avail);
             } else if (s->kind == ST_WHILE)
                 changed |= cse_list(s->body, avail);
+        }
+        return changed;
+    }
+
+    // ------------------------------------------------ loop-carried values
+    // irgen lays `while c do b end` out rotated: the condition's statements once in front of the loop and again at the end
+    // of the body, for the next iteration's test.  An escape-time loop (`while abs(c) < 2 ... c = c*c + p`) then computes
+    // the squares of the NEW c for the test at the end of iteration k-1 and the squares of the SAME numbers, now read
+    // through the loop's phis, for the product at the top of iteration k.  For a pure top-level body statement
+    // S = op(args) whose arguments are phis of this loop, constants and values defined outside it: when op(entry values)
+    // is available in front of the loop (E) and op(back-edge values) is a top-level body statement (B, executed in every
+    // iteration), then S in iteration k is B of iteration k-1 -- the same pure op on the same operand values -- and E in
+    // the first one.  A new phi(E, B) carries the value and S becomes a copy of it.  Bit-exact by construction (nothing
+    // is re-associated, only not computed twice); Render/Mandelbrot.mm loses 4 of its 14 products per iteration.
+    bool loop_carry_enabled = loop_carry_default();
+    static bool loop_carry_default() {
+        const char *e = getenv("MMB_LOOP_CARRY");  // 0 switches the pass off (what a comparison against the plain IR needs)
+        return e ? atoi(e) != 0 : true;
+    }
+    static bool defined_inside(const Value *v, const Stmt *loop) {
+        for (const Stmt *s = v->def; s; s = s->parent)
+            if (s == loop) return true;
+        return false;
+    }
+    // the back-edge operand of a loop phi is a copy (`x.2 = tmp`) that copy propagation, visiting the phi first, leaves alone
+    static P through_copies(P p) {
+        for (int n = 0; n < 64 && !p.is_const && p.value->def && p.value->def->kind == ST_ASSIGN && p.value->def->rhs->kind == RHS_PRIMARY; ++n)
+            p = p.value->def->rhs->prim;
+        return p;
+    }
+    static bool scalar_result(const Rhs *r) {
+        if (r->kind != RHS_OP || !r->op->pure) return false;
+        if (r->op->prop != TP_CONST) return true;  // max of the (scalar) argument types
+        return r->op->type == T_INT || r->op->type == T_FLOAT || r->op->type == T_COMPLEX;
+    }
+    bool loop_carried_values(Stmt *s, std::map<std::string, Value *> avail) {
+        bool changed = false;
+        for (; s; s = s->next) {
+            if (s->kind == ST_ASSIGN) {
+                if (s->rhs->kind == RHS_OP && s->rhs->op->pure) avail.emplace(rhs_key(s->rhs), s->lhs);
+            } else if (s->kind == ST_IF) {
+                changed |= loop_carried_values(s->cons, avail);
+                changed |= loop_carried_values(s->alt, avail);
+            } else if (s->kind == ST_WHILE) {
+                std::unordered_map<const Value *, std::pair<P, P>> phis;  // phi -> (value on entry, value on the back edge)
+                for (Stmt *p = s->entry; p; p = p->next)
+                    if (p->kind == ST_PHI && p->rhs->kind == RHS_PRIMARY && p->rhs2->kind == RHS_PRIMARY)
+                        phis[p->lhs] = {through_copies(p->rhs->prim), through_copies(p->rhs2->prim)};
+                std::map<std::string, Value *> in_body;
+                for (Stmt *b = s->body; b; b = b->next)
+                    if (b->kind == ST_ASSIGN && scalar_result(b->rhs)) in_body.emplace(rhs_key(b->rhs), b->lhs);
+                for (Stmt *c = s->body; c; c = c->next) {
+                    if (c->kind != ST_ASSIGN || !scalar_result(c->rhs)) continue;
+                    std::string on_entry = std::string("O:") + c->rhs->op->name, on_back = on_entry;
+                    bool reads_phi = false, ok = true;
+                    for (auto &a : c->rhs->args) {
+                        auto it = a.is_const ? phis.end() : phis.find(a.value);
+                        if (it != phis.end()) {
+                            reads_phi = true;
+                            on_entry += "," + primary_to_string(it->second.first);
+                            on_back += "," + primary_to_string(it->second.second);
+                        } else if (!a.is_const && defined_inside(a.value, s)) {
+                            ok = false;
+                            break;
+                        } else {
+                            on_entry += "," + primary_to_string(a);
+                            on_back += "," + primary_to_string(a);
+                        }
+                    }
+                    if (!ok || !reads_phi) continue;
+                    auto e = avail.find(on_entry);
+                    auto b = in_body.find(on_back);
+                    if (e == avail.end() || b == in_body.end() || b->second == c->lhs) continue;
+                    int top_id = 0;
+                    for (auto &existing : code.compvars) top_id = std::max(top_id, existing.id);
+                    CompVar *cv = g.temp(T_INT);  // propagate_types gives it the operands' type
+                    cv->id = top_id + 1;          // loaded IR keeps the ids of its text: stay clear of them
+                    Value *carried = code.new_value(cv);
+                    carried->index = 1;
+                    Stmt *phi = code.new_stmt(ST_PHI);
+                    phi->lhs = carried;
+                    carried->def = phi;
+                    phi->rhs = g.rhs_prim(P::of(e->second));
+                    phi->rhs2 = g.rhs_prim(P::of(b->second));
+                    add_use(e->second, phi);
+                    add_use(b->second, phi);
+                    phi->parent = s;
+                    phi->next = s->entry;
+                    s->entry = phi;
+                    replace_rhs(&c->rhs, g.rhs_prim(P::of(carried)), c);
+                    changed = true;
+                }
+                changed |= loop_carried_values(s->body, avail);
+            }
         }
         return changed;
     }
@@ -516,6 +611,11 @@ struct Optimizer {
             changed |= make_tuple();
             changed |= cse_list(first, {});
             changed |= copy_propagation();
+            if (loop_carry_enabled) {
+                fix_parents(first, nullptr);
+                changed |= loop_carried_values(first, {});
+                changed |= copy_propagation();
+            }
             changed |= constant_folding();
             changed |= simplify_ops();
             changed |= orig_val_resize(&first);
@@ -544,6 +644,25 @@ Stmt *strip_nils(Stmt *s) {
 }
 
 }  // namespace
+
+// The loop-carried value pass alone, for IR that did not come through this front end (mmb_load_ir: the reference's own
+// compiler hands its optimised IR over the boundary and must end up with the same kernels).  A fixpoint on IR that has
+// already been through it.
+void carry_loop_values(Module &mod, FilterCode &code) {
+    Gen g(mod, code);
+    Optimizer opt{mod, g, code, code.filter, code.first};
+    if (!opt.loop_carry_enabled) return;
+    Optimizer::fix_parents(code.first, nullptr);
+    bool changed = false;
+    for (int iter = 0; iter < 16 && opt.loop_carried_values(code.first, {}); ++iter) {
+        changed = true;
+        opt.copy_propagation();
+        opt.dead_assignments();
+    }
+    if (!changed) return;
+    code.first = strip_nils(code.first);
+    Optimizer::fix_parents(code.first, nullptr);
+}
 
 // -------------------------------------------------------------------- types
 void propagate_types(FilterCode &code) {
