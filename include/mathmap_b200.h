@@ -36,6 +36,8 @@ enum { MMB_EDGE_COLOR = 0, MMB_EDGE_WRAP = 1, MMB_EDGE_REFLECT = 2, MMB_EDGE_ROT
  * mmb_load_ir: the same from IR text ("mmir 1", see csrc/ir/ir_text.cpp) that a
  *   reference-side backends/cuda.c prints from filter_code_t**.  Replaces
  *   gen_and_load_c_code (backends/cc.c:634-758, declared compiler.h:79-82).
+ * Both run the loop-carried value pass (csrc/ir/passes.cpp; environment MMB_LOOP_CARRY=0 switches it off), so the
+ *   reference compiler's IR ends in the same kernels as mmb_compile's.
  * Both return NULL on error with the message in mmb_last_error().  NVRTC
  * compilation for sm_100a happens lazily at the first render of a given
  * sampler/edge/output configuration.

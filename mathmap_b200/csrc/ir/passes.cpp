@@ -244,8 +244,8 @@ struct Optimizer {
     }
 
     // ------------------------------------------------ loop-carried values
-    // irgen lays `while c do b end` out rotated: the condition's statements once in front of the loop and again at the end
-    // of the body, for the next iteration's test.  An escape-time loop (`while abs(c) < 2 ... c = c*c + p`) then computes
+    // irgen lays `while c do b end` out rotated, as the reference does (compiler.c:2119-2137): the condition's statements
+    // once in front of the loop and again at the end of the body, for the next iteration's test.  An escape-time loop (`while abs(c) < 2 ... c = c*c + p`) then computes
     // the squares of the NEW c for the test at the end of iteration k-1 and the squares of the SAME numbers, now read
     // through the loop's phis, for the product at the top of iteration k.  For a pure top-level body statement
     // S = op(args) whose arguments are phis of this loop, constants and values defined outside it: when op(entry values)
