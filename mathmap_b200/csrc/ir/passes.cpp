@@ -269,10 +269,12 @@ struct Optimizer {
             p = p.value->def->rhs->prim;
         return p;
     }
+    // scalar arithmetic only: conversions, + - * / %, the math functions, comparisons, and the complex functions -- whose
+    // operands and results are ints, floats or complex numbers (no tuples, tree vectors, images or colours)
     static bool scalar_result(const Rhs *r) {
         if (r->kind != RHS_OP || !r->op->pure) return false;
-        if (r->op->prop != TP_CONST) return true;  // max of the (scalar) argument types
-        return r->op->type == T_INT || r->op->type == T_FLOAT || r->op->type == T_COMPLEX;
+        const int id = r->op->id;
+        return (id >= OP_INT2FLOAT && id <= OP_NOT) || (id >= OP_COMPLEX && id <= OP_C_GAMMA);
     }
     bool loop_carried_values(Stmt *s, std::map<std::string, Value *> avail) {
         bool changed = false;

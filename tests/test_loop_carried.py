@@ -158,3 +158,48 @@ def test_the_compiled_mandelbrot_loop_is_33_instructions(tmp_path):
     hot = [c for c in loops if c["FMUL"] >= 8]
     assert len(hot) == 1, loops
     assert hot[0]["FMUL"] == 10 and hot[0]["FADD"] == 19 and sum(hot[0].values()) == 33, hot[0]
+
+
+def test_compositions_with_an_escape_loop_inside():
+    """Seeded two- and three-node compositions whose first node is one of the Mandelbrot filters: the loop ends up inlined into
+    other filters' sampling code (closures, filter calls, other loops).  The pass changes every one of these IRs; the oracle
+    renders the same bytes with and without it."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_compositions as fc
+    from conftest import synthetic_rgba
+    rng = random.Random(5)
+    filters = fc.catalogue()
+    with_img = [f for f in filters if f[1]]
+    loops = [f for f in filters if "andelbrot" in f[0]]
+    assert len(loops) == 2
+    W, H = 80, 56
+    imgs = [synthetic_rgba(W, H, seed=s) for s in (1, 2, 3)]
+    done = 0
+    while done < 8:
+        a, b = rng.choice(loops), rng.choice(with_img)
+        nodes = '(node :name "a" :type "%s" :input-slots ()) (node :name "b" :type "%s" :input-slots (("%s" "a" "out")))' % (a[0], b[0], rng.choice(b[1]))
+        root = "b"
+        if rng.random() < 0.4:
+            c = rng.choice(with_img)
+            if c[0] in (a[0], b[0]):
+                continue
+            nodes += ' (node :name "c" :type "%s" :input-slots (("%s" "b" "out")))' % (c[0], rng.choice(c[1]))
+            root = "c"
+        design = '(design %s :name "comp" :root "%s")' % (nodes, root)
+        try:
+            src = mb.design_to_source(design, fc.EX)
+            plain, carried = ir_of(src, False), ir_of(src, True)
+        except mb.MathMapError:
+            continue  # e.g. an argument name defined twice in the generated source
+        done += 1
+        assert plain != carried, design
+        vals, k = {}, 0
+        for name, kind, _lo, _hi, _default in mb.Module(ir=carried).uservals():
+            if kind == mb.USERVAL_IMAGE:
+                vals[name] = imgs[k % 3]
+                k += 1
+        t, aa = rng.choice([0.0, 0.3, 0.75]), bool(rng.getrandbits(1))
+        assert np.array_equal(OracleFilter(plain).render(W, H, vals, t=t, antialiasing=aa),
+                              OracleFilter(carried).render(W, H, vals, t=t, antialiasing=aa)), design
