@@ -311,6 +311,14 @@ struct Optimizer {
                         }
                     }
                     if (!ok || !reads_phi) continue;
+                    // S may only be read inside the loop: behind it, S is the last EXECUTED iteration's value while the
+                    // carrying phi already holds the next one's
+                    for (const Stmt *u : c->lhs->uses) {
+                        const Stmt *up = u;
+                        while (up && up != s) up = up->parent;
+                        if (!up) { ok = false; break; }
+                    }
+                    if (!ok) continue;
                     auto e = avail.find(on_entry);
                     auto b = in_body.find(on_back);
                     if (e == avail.end() || b == in_body.end() || b->second == c->lhs) continue;

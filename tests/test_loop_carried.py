@@ -70,6 +70,12 @@ SHAPES = {
     # a loop inside a loop, both with carried parts
     "nested": ("filter m ()\n  p = x; i = 0; acc = 0;\n  while p*p < 2 && i < 6 do\n    b = y; j = 0;\n    while b*b + p*p < 3 && j < 5 do\n      b = b*b + p*p - 0.3;\n      j = j + 1\n    end;\n"
                "    acc = acc + j;\n    p = p*p + 0.2;\n    i = i + 1\n  end;\n  grayColor(acc / 30)\nend\n"),
+    # the carried product is also a variable that is read behind the loop (its own phi keeps the last executed iteration's)
+    "read_after": ("filter ra ()\n  v = x * 1.3; q = 0; n = 0;\n  while v*v < 2.5 && n < 12 do\n    q = v*v;\n    v = q + y * 0.5 + 0.1;\n    n = n + 1\n  end;\n"
+                   "  rgba:[q * 0.3, v * 0.2, n / 12, 1]\nend\n"),
+    # a swap in the loop: phis whose back-edge operands are other phis' values
+    "swap": ("filter sw ()\n  p = x; q = y; n = 0;\n  while p*p + q*q < 3 && n < 9 do\n    s = p*p - q*q + 0.3;\n    p = q;\n    q = s;\n    n = n + 1\n  end;\n"
+             "  rgba:[p * 0.3 + 0.5, q * 0.3 + 0.5, n / 9, 1]\nend\n"),
     # a frame-constant loop (evaluated by the host replay / once per frame)
     "frame_constant": ("filter c (float k: 0-2 (0.7))\n  v = k; n = 0;\n  while v*v < 50 && n < 20 do\n    v = v*v + k;\n    n = n + 1\n  end;\n  grayColor(n / 20 + x * 0.1)\nend\n"),
 }
