@@ -94,7 +94,7 @@ def test_loop_shapes_with_and_without_the_pass(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(SHAPES))
+@pytest.mark.parametrize("name", ["frame_constant", "invariant", "julia", "nested"])
 def test_loop_shapes_on_the_device(name):
     src = SHAPES[name]
     m = mb.Module(source=src)
