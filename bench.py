@@ -66,6 +66,7 @@ HEADLINE = "mandelbrot"
 # an all-issue-slots-busy kernel reaches 29/33 = 0.879 of this roofline.  (Rounds 1-2 counted the IR's 20 MUL + 19 ADD = 39,
 # of which the loop then executed 14 + 19 in 37 instructions; SURVEY.md section 8d's 45 includes the NEGs.)
 MANDELBROT_FLOPS_PER_ITERATION = 29
+MANDELBROT_LOOP_INSTRUCTIONS = 33
 # The blur's recursion (gauss.c:175-196): per step 9 DMUL + 4 DSUB + 5 DADD = 18 double operations, + 1 DADD for vp + vm per
 # output sample (half a DADD per sweep step); 2 passes x 2 sweeps x 4 channels steps per pixel.  No FMA (bit parity with the host).
 GAUSS_FP64_OPS_PER_PIXEL = 2 * 2 * 4 * 18.5
@@ -416,6 +417,9 @@ def measure(name, ctx, args, with_cpu):
         peak_tflops = B200_SMS * FP32_LANES_PER_SM * sm_mhz * 1e6 / 1e12
         achieved = MANDELBROT_FLOPS_PER_ITERATION * my_iters / (kernel_ms / 1e3) / 1e12
         res["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                           # the same time counted in issue slots: the loop's 33 instructions per iteration (tests/test_loop_carried.py
+                           # reads them from the cubin) against one warp instruction per SM sub-partition and clock
+                           "issue_slots_frac": achieved / peak_tflops * MANDELBROT_LOOP_INSTRUCTIONS / MANDELBROT_FLOPS_PER_ITERATION,
                            "traffic": traffic,
                            "note": "non-FMA FP32 issue roofline: 148 SMs x 128 lanes x %.0f MHz (median SM clock under load); "
                                    "29 distinct float operations (10 MUL + 19 ADD) per iteration of the quaternion loop, 33 SASS instructions with the loop control (issue-slot ceiling 29/33 = 0.879) x %d iterations per launch on this rank; output writes are %.1f GB/s of the %s %.0f GB/s HBM peak; "
