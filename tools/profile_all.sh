@@ -18,4 +18,7 @@ for w in mandelbrot twirl droste sea ident invert perlin; do
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gauss_iir -c 2 -s 2 -o "$OUT/prof_gauss" -f \
     python bench.py --workload gauss --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/ncu_full_gauss.log" 2>&1
+# A/B of the loop-carried value pass on the headline kernel (one process, same box)
+python tools/time_kernel.py "tests/golden/filters/examples/Render/Mandelbrot.mm" 16384 16384 num_iterations=256 --launches 5 --env MMB_LOOP_CARRY=0,1 \
+    > "$OUT/loop_carry_ab.json" 2> "$OUT/loop_carry_ab.err"
 ls -la "$OUT"
