@@ -245,14 +245,15 @@ struct Optimizer {
 
     // ------------------------------------------------ loop-carried values
     // irgen lays `while c do b end` out rotated, as the reference does (compiler.c:2119-2137): the condition's statements
-    // once in front of the loop and again at the end of the body, for the next iteration's test.  An escape-time loop (`while abs(c) < 2 ... c = c*c + p`) then computes
-    // the squares of the NEW c for the test at the end of iteration k-1 and the squares of the SAME numbers, now read
-    // through the loop's phis, for the product at the top of iteration k.  For a pure top-level body statement
-    // S = op(args) whose arguments are phis of this loop, constants and values defined outside it: when op(entry values)
-    // is available in front of the loop (E) and op(back-edge values) is a top-level body statement (B, executed in every
-    // iteration), then S in iteration k is B of iteration k-1 -- the same pure op on the same operand values -- and E in
-    // the first one.  A new phi(E, B) carries the value and S becomes a copy of it.  Bit-exact by construction (nothing
-    // is re-associated, only not computed twice); Render/Mandelbrot.mm loses 4 of its 14 products per iteration.
+    // once in front of the loop and again at the end of the body, for the next iteration's test.  An escape-time loop
+    // (`while abs(c) < 2 ... c = c*c + p`) then computes the squares of the NEW c for the test at the end of iteration k-1
+    // and the squares of the SAME numbers, now read through the loop's phis, for the product at the top of iteration k.
+    // For a pure top-level body statement S = op(args) whose arguments are phis of this loop, constants and values defined
+    // outside it: when op(entry values) is available in front of the loop (E) and op(back-edge values) is a top-level body
+    // statement (B, executed in every iteration), then S in iteration k is B of iteration k-1 -- the same pure op on the
+    // same operand values -- and E in the first one.  A new phi(E, B) carries the value and S becomes a copy of it.
+    // Bit-exact by construction (nothing is re-associated, only not computed twice); Render/Mandelbrot.mm loses 4 of its
+    // 14 products per iteration (27.16 -> 24.21 ms at 16384 x 16384 on a B200, profiles/r02_loop_carry_ab.json).
     bool loop_carry_enabled = loop_carry_default();
     static bool loop_carry_default() {
         const char *e = getenv("MMB_LOOP_CARRY");  // 0 switches the pass off (what a comparison against the plain IR needs)
