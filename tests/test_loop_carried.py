@@ -209,3 +209,13 @@ def test_compositions_with_an_escape_loop_inside():
         t, aa = rng.choice([0.0, 0.3, 0.75]), bool(rng.getrandbits(1))
         assert np.array_equal(OracleFilter(plain).render(W, H, vals, t=t, antialiasing=aa),
                               OracleFilter(carried).render(W, H, vals, t=t, antialiasing=aa)), design
+
+
+def test_random_loop_filters_with_and_without_the_pass():
+    """tools/fuzz_loops.py (any seed and count; profiles/r02_fuzz_loops.log keeps a run of 600): random loops whose conditions
+    share subexpressions with their bodies, chains of carried values, nested loops."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_loops
+    done, changed, failures = fuzz_loops.run(3, 30)
+    assert done == 30 and changed >= 10 and not failures, failures
