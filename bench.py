@@ -70,6 +70,9 @@ MANDELBROT_LOOP_INSTRUCTIONS = 33
 # The blur's recursion (gauss.c:175-196): per step 9 DMUL + 4 DSUB + 5 DADD = 18 double operations, + 1 DADD for vp + vm per
 # output sample (half a DADD per sweep step); 2 passes x 2 sweeps x 4 channels steps per pixel.  No FMA (bit parity with the host).
 GAUSS_FP64_OPS_PER_PIXEL = 2 * 2 * 4 * 18.5
+# Render/Perlin Noise.mm, 5 octaves: per octave 8 lattice corners x 4 products + 3 axes x 9 (7th-order blend) + 7 interpolations x 2
+# + 5 (octave bookkeeping) = 78 DMUL, and 42 DADD (mm_noise.cuh; profiles/r02_perlin_sass_hist.txt: 390 DMUL + 210 DADD per pixel executed)
+PERLIN_FP64_OPS_PER_PIXEL = 5 * (78 + 42)
 B200_SMS, FP32_LANES_PER_SM, FP64_LANES_PER_SM = 148, 128, 64
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 
@@ -447,6 +450,15 @@ def measure(name, ctx, args, with_cpu):
                                     "note": "non-FMA FP64 issue roofline: 148 SMs x 64 lanes x %.0f MHz; 18.5 double operations per recursion step x "
                                             "2 passes x 2 sweeps x 4 channels per pixel (gauss.c:175-196; recomputed steps are not counted); the exact recursion "
                                             "makes this the binding roofline, the HBM one above is what SURVEY.md section 8d asks for" % sm_mhz}
+        if name == "perlin":
+            ops = PERLIN_FP64_OPS_PER_PIXEL * W * my_rows
+            peak64 = B200_SMS * FP64_LANES_PER_SM * sm_mhz * 1e6 / 1e12
+            ach64 = ops / (kernel_ms / 1e3) / 1e12
+            res["roofline_fp64"] = {"bound": "fp64", "achieved": ach64, "peak": peak64, "unit": "TFLOP/s", "frac": ach64 / peak64,
+                                    "note": "non-FMA FP64 issue roofline: 148 SMs x 64 lanes x %.0f MHz; 5 octaves x (78 products + 42 sums) in double per pixel "
+                                            "(libnoise 1.0.0 gradient noise with the 7th-order blend: csrc/runtime/mm_noise.cuh; the executed DMUL / DADD counts of "
+                                            "profiles/r02_perlin_sass_hist.txt are exactly these, nothing is recomputed); compares and int<->double conversions, which "
+                                            "share the pipe, are not counted" % sm_mhz}
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region:
     # H2D of the step's input (at N > 1 one band of rows per rank, then one NCCL all-gather), mmb_init_frame, mmb_calc_lines into host memory
